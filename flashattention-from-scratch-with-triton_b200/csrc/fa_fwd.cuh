@@ -1,0 +1,360 @@
+// Forward attention for sm_100a:  O = softmax(Q K^T * scale [+causal]) V,  LSE = m + ln(l).
+// Replaces flash_attention_forward_kernel (reference code/_flash_attention_kernel_optimized.py:34-129)
+// with a persistent, warp-specialized tcgen05 / TMA kernel.
+//
+// CTA = 320 threads, one CTA per SM, each work item = 256 query rows of one (batch, head):
+//   warps 0-3  softmax warpgroup for Q tile 0 (rows 0..127 of the item; thread r <-> TMEM lane r)
+//   warps 4-7  softmax warpgroup for Q tile 1
+//   warp  8    MMA issuer (one thread): S_t = Q_t K^T, O_t += P_t V on tcgen05, accumulators in TMEM
+//   warp  9    TMA producer (one thread) + dynamic tile scheduler
+// TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D); P_t (16-bit) overwrites
+// the first 64 columns of S_t and is consumed as the A operand straight from TMEM.
+// The two tiles ping-pong: while warpgroup 0 runs softmax on S0(j+1), the tensor core runs
+// P1(j) V(j) and S1(j+1).
+#pragma once
+#include "fa_ptx.cuh"
+
+namespace fa {
+
+struct FwdParams {
+    int BH, Sq, Sk;
+    int n_qblk;            // ceil(Sq / 256)
+    int n_items;           // BH * n_qblk
+    int causal;
+    float scale;           // softmax scale (1/sqrt(D) by default)
+    float scale_log2;      // scale * log2(e)
+    float* lse;            // [BH, Sq] fp32
+    unsigned int* sched;   // work counter, zeroed before launch
+};
+
+template <int D> struct FwdCfg {
+    static constexpr int kChunks = D / 64;                 // 64-element (128-byte) column chunks
+    static constexpr int kTileBytes = 128 * D * 2;         // one 128-row Q / K / V tile
+    static constexpr int kStages = (D == 128) ? 4 : 6;     // K/V ring slots
+    static constexpr int kOStageBytes = 128 * 128;         // [128 rows][64 cols] staging per warpgroup
+    static constexpr int kOffQ = 0;
+    static constexpr int kOffKV = 2 * kTileBytes;
+    static constexpr int kOffO = kOffKV + kStages * kTileBytes;
+    static constexpr int kOffBar = kOffO + 2 * kOStageBytes;
+    static constexpr int kNumBars = 2 + 2 + 2 * kStages + 2 + 2 + 2 + 2 + 2 + 2;
+    static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 64 + 1024;   // +1024: manual alignment slack
+};
+
+constexpr int kFwdThreads = 320;
+constexpr float kLazyRescaleLog2 = 8.0f;   // rescale O only when the row max grows by > 2^8 in exp2 units
+
+// iterations (128-wide K/V tiles) that tile `t` of the item starting at row q0 must visit
+__device__ __forceinline__ int fwd_tile_iters(int q0, int t, int Sq, int Sk, int causal) {
+    const int r0 = q0 + t * 128;
+    if (r0 >= Sq) return 0;
+    const int nkv = (Sk + 127) >> 7;
+    if (!causal) return nkv;
+    const int last_row = min(r0 + 127, Sq - 1);          // top-left aligned: row i sees cols <= i
+    const int n = (min(last_row, Sk - 1) >> 7) + 1;
+    return min(n, nkv);
+}
+
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+              const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapO,
+              const FwdParams p) {
+    using C = FwdCfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + C::kOffQ;
+    uint8_t* sKV = smem + C::kOffKV;
+    uint8_t* sO = smem + C::kOffO;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+    uint64_t* q_full = bars;                    // [2]  TMA -> MMA
+    uint64_t* q_empty = bars + 2;               // [2]  MMA -> TMA
+    uint64_t* kv_full = bars + 4;               // [kStages]
+    uint64_t* kv_empty = kv_full + C::kStages;  // [kStages]
+    uint64_t* s_full = kv_empty + C::kStages;   // [2]  MMA -> softmax (S_t ready; also: all earlier MMAs done)
+    uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA (P_t in TMEM, O_t rescaled)
+    uint64_t* o_full = p_full + 2;              // [2]  MMA -> softmax (last P V of the item done)
+    uint64_t* o_empty = o_full + 2;             // [2]  softmax -> MMA (O_t drained from TMEM)
+    uint64_t* sched_full = o_empty + 2;         // [2]
+    uint64_t* sched_empty = sched_full + 2;     // [2]
+    volatile int* sched_item = reinterpret_cast<volatile int*>(sched_empty + 2);   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sched_item) + 2);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
+            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 128);
+            mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 9);   // MMA thread + 8 softmax warps
+        }
+        for (int i = 0; i < C::kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 9) {
+        // ================================ TMA producer + scheduler ================================
+        if (lane_id() == 0) {
+            tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV);
+            uint32_t kv_cnt = 0;        // K/V tiles produced so far
+            uint32_t q_cnt0 = 0, q_cnt1 = 0;
+            int item = blockIdx.x;
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t slot = it & 1;
+                mbar_wait(&sched_empty[slot], ((it >> 1) & 1) ^ 1, 100);
+                sched_item[slot] = item;
+                mbar_arrive(&sched_full[slot]);
+                if (item >= p.n_items) break;
+                const int bh = item / p.n_qblk;
+                const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;   // heavy (late) query blocks first
+                const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
+                const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
+                const int n = max(n0, n1);
+                auto load_q = [&](int t, uint32_t& cnt) {
+                    mbar_wait(&q_empty[t], (cnt & 1) ^ 1, 101 + t);
+                    mbar_arrive_expect_tx(&q_full[t], C::kTileBytes);
+                    #pragma unroll
+                    for (int c = 0; c < C::kChunks; ++c)
+                        tma_load_3d(sQ + t * C::kTileBytes + c * 16384, &mapQ, &q_full[t], c * 64, q0 + t * 128, bh);
+                    ++cnt;
+                };
+                auto load_kv = [&](const CUtensorMap* m, int j) {
+                    const uint32_t st = kv_cnt % C::kStages;
+                    mbar_wait(&kv_empty[st], ((kv_cnt / C::kStages) & 1) ^ 1, 110);
+                    mbar_arrive_expect_tx(&kv_full[st], C::kTileBytes);
+                    #pragma unroll
+                    for (int c = 0; c < C::kChunks; ++c)
+                        tma_load_3d(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, j * 128, bh);
+                    ++kv_cnt;
+                };
+                if (n0 > 0) load_q(0, q_cnt0);
+                load_kv(&mapK, 0);
+                if (n1 > 0) load_q(1, q_cnt1);
+                load_kv(&mapV, 0);
+                for (int j = 1; j < n; ++j) { load_kv(&mapK, j); load_kv(&mapV, j); }
+                item = (int)atomicAdd(p.sched, 1u) + (int)gridDim.x;
+            }
+        }
+    } else if (warp == 8) {
+        // ======================================= MMA issuer =======================================
+        if (lane_id() == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBf16, false, false, 128, 128);
+            constexpr uint32_t idesc_pv = make_idesc(kBf16, false, true, 128, D);
+            const uint32_t sq_addr = smem_u32(sQ), skv_addr = smem_u32(sKV);
+            uint32_t kv_cnt = 0;
+            uint32_t ph_q = 0, ph_p = 0, ph_oe = 0;      // bit t = parity to wait for next
+            auto kv_wait = [&](uint32_t cnt) {
+                mbar_wait(&kv_full[cnt % C::kStages], (cnt / C::kStages) & 1, 200);
+            };
+            auto issue_s = [&](int t, uint32_t st) {   // S_t = Q_t K^T
+                const uint32_t a = sq_addr + t * C::kTileBytes, b = skv_addr + st * C::kTileBytes;
+                #pragma unroll
+                for (int k = 0; k < D / 16; ++k) {
+                    const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+                    umma_ss(tmem + t * 128, make_smem_desc(a + off, 0, 1024), make_smem_desc(b + off, 0, 1024),
+                            idesc_s, k > 0);
+                }
+            };
+            auto issue_pv = [&](int t, uint32_t st, bool acc) {   // O_t (+)= P_t V
+                const uint32_t b = skv_addr + st * C::kTileBytes;
+                #pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_ts(tmem + 256 + t * D, tmem + t * 128 + k * 8, make_smem_desc(b + k * 2048, 16384, 1024),
+                            idesc_pv, acc || k > 0);
+            };
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t slot = it & 1;
+                mbar_wait(&sched_full[slot], (it >> 1) & 1, 201);
+                const int item = sched_item[slot];
+                mbar_arrive(&sched_empty[slot]);
+                if (item >= p.n_items) break;
+                const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
+                const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
+                const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
+                const int n = max(n0, n1);
+                // ---- S_t(0)
+                {
+                    const uint32_t st = kv_cnt % C::kStages;
+                    kv_wait(kv_cnt);
+                    if (n0 > 0) {
+                        mbar_wait(&q_full[0], ph_q & 1, 202); ph_q ^= 1; tc_fence_after();
+                        issue_s(0, st); tc_commit(&s_full[0]);
+                        if (n0 == 1) tc_commit(&q_empty[0]);
+                    }
+                    if (n1 > 0) {
+                        mbar_wait(&q_full[1], (ph_q >> 1) & 1, 203); ph_q ^= 2; tc_fence_after();
+                        issue_s(1, st); tc_commit(&s_full[1]);
+                        if (n1 == 1) tc_commit(&q_empty[1]);
+                    }
+                    tc_commit(&kv_empty[st]); ++kv_cnt;
+                }
+                for (int j = 0; j < n; ++j) {
+                    const uint32_t vst = kv_cnt % C::kStages;
+                    const uint32_t kst = (kv_cnt + 1) % C::kStages;
+                    const bool more = (j + 1 < n);
+                    kv_wait(kv_cnt);                       // V(j)
+                    if (j < n0) {
+                        mbar_wait(&p_full[0], ph_p & 1, 204); ph_p ^= 1;
+                        if (j == 0) { mbar_wait(&o_empty[0], (ph_oe & 1) ^ 1, 205); ph_oe ^= 1; }
+                        tc_fence_after();
+                        issue_pv(0, vst, j > 0);
+                        if (j == n0 - 1) tc_commit(&o_full[0]);
+                    }
+                    if (more) kv_wait(kv_cnt + 1);         // K(j+1)
+                    if (j + 1 < n0) {
+                        tc_fence_after();
+                        issue_s(0, kst); tc_commit(&s_full[0]);
+                        if (j + 1 == n0 - 1) tc_commit(&q_empty[0]);
+                    }
+                    if (j < n1) {
+                        mbar_wait(&p_full[1], (ph_p >> 1) & 1, 206); ph_p ^= 2;
+                        if (j == 0) { mbar_wait(&o_empty[1], ((ph_oe >> 1) & 1) ^ 1, 207); ph_oe ^= 2; }
+                        tc_fence_after();
+                        issue_pv(1, vst, j > 0);
+                        if (j == n1 - 1) tc_commit(&o_full[1]);
+                    }
+                    tc_commit(&kv_empty[vst]); ++kv_cnt;
+                    if (more) {
+                        if (j + 1 < n1) {
+                            issue_s(1, kst); tc_commit(&s_full[1]);
+                            if (j + 1 == n1 - 1) tc_commit(&q_empty[1]);
+                        }
+                        tc_commit(&kv_empty[kst]); ++kv_cnt;
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================= softmax warpgroups (0,1) ================================
+        const int t = warp >> 2;                       // Q tile handled by this warpgroup
+        const int r = tid & 127;                       // row inside the tile == TMEM lane
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem + lane_field + t * 128;
+        const uint32_t tO = tmem + lane_field + 256 + t * D;
+        uint8_t* sOt = sO + t * C::kOStageBytes;
+        uint32_t ph_s = 0, ph_o = 0;
+        const float c2 = p.scale_log2;
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t slot = it & 1;
+            mbar_wait(&sched_full[slot], (it >> 1) & 1, 300);
+            const int item = sched_item[slot];
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&sched_empty[slot]);
+            if (item >= p.n_items) break;
+            const int bh = item / p.n_qblk;
+            const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
+            const int nt = fwd_tile_iters(q0, t, p.Sq, p.Sk, p.causal);
+            if (nt == 0) continue;
+            const int row_g = q0 + t * 128 + r;
+            float m = -INFINITY, l = 0.f;
+            for (int j = 0; j < nt; ++j) {
+                mbar_wait(&s_full[t], ph_s, 301); ph_s ^= 1;
+                tc_fence_after();
+                uint32_t s[4][32];
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, s[q]);
+                tc_wait_ld();
+                // element mask only on tiles that straddle the diagonal or the end of K
+                int cmax = p.Sk - 1 - j * 128;                              // last valid column in this tile
+                if (p.causal) cmax = min(cmax, row_g - j * 128);
+                if (cmax < 127) {
+                    #pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        #pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (q * 32 + i > cmax) s[q][i] = 0xff800000u;  // -inf
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                #pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[0][i])); mx1 = fmaxf(mx1, __uint_as_float(s[1][i]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[2][i])); mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
+                }
+                const float m_new = fmaxf(fmaxf(m, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+                if (j == 0) {
+                    m = m_new;
+                } else {
+                    // lazy rescale (warp-uniform decision: tcgen05.ld/st are warp-collective)
+                    const bool need = (m_new - m) * c2 > kLazyRescaleLog2;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float corr = ex2_approx((m - m_new) * c2);     // m = -inf -> 0
+                        l *= corr;
+                        #pragma unroll
+                        for (int q = 0; q < D / 32; ++q) {
+                            uint32_t o[32];
+                            tmem_ld32(tO + q * 32, o);
+                            tc_wait_ld();
+                            #pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                            tmem_st32(tO + q * 32, o);
+                        }
+                        m = m_new;
+                    }
+                }
+                const float neg_mc = (m == -INFINITY) ? 0.f : -m * c2;
+                float l0 = 0.f, l1 = 0.f;
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t pk[16];
+                    #pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[q][2 * i]), c2, neg_mc));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[q][2 * i + 1]), c2, neg_mc));
+                        l0 += p0; l1 += p1;                                  // fp32, before rounding (ref :111)
+                        pk[i] = pack2<kBf16>(p0, p1);
+                    }
+                    tmem_st16(tS + q * 16, pk);
+                }
+                l += l0 + l1;
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(&p_full[t]);
+            }
+            // ---------------- epilogue: O = o / l, LSE = m*scale + ln(l) ----------------
+            mbar_wait(&o_full[t], ph_o, 302); ph_o ^= 1;
+            tc_fence_after();
+            const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
+            #pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) {
+                uint32_t o[2][32];
+                tmem_ld32(tO + c * 64, o[0]);
+                tmem_ld32(tO + c * 64 + 32, o[1]);
+                tc_wait_ld();
+                if (c == C::kChunks - 1) { tc_fence_before(); mbar_arrive(&o_empty[t]); }
+                #pragma unroll
+                for (int g = 0; g < 8; ++g) {          // 8 x 16-byte groups = 64 columns
+                    uint32_t w[4];
+                    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int e = g * 8 + 2 * i;
+                        w[i] = pack2<kBf16>(__uint_as_float(o[e >> 5][e & 31]) * inv_l,
+                                            __uint_as_float(o[(e + 1) >> 5][(e + 1) & 31]) * inv_l);
+                    }
+                    *reinterpret_cast<uint4*>(sOt + sw128_offset(r, g)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1 + t, 128);
+                if (r == 0) {
+                    tma_store_3d(&mapO, sOt, c * 64, q0 + t * 128, bh);
+                    tma_store_commit();
+                    tma_store_wait_read0();
+                }
+                named_bar_sync(1 + t, 128);
+            }
+            if (row_g < p.Sq)
+                p.lse[(size_t)bh * p.Sq + row_g] = (l > 0.f) ? fmaf(m, p.scale, __logf(l)) : -INFINITY;
+        }
+        if (r == 0) tma_store_wait_all0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fa
