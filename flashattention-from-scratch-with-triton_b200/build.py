@@ -1,0 +1,82 @@
+"""Build the sm_100a CUDA library (and the bring-up binary) in-tree with nvcc.
+
+    python flashattention-from-scratch-with-triton_b200/build.py [--force] [--bringup] [-v]
+
+Outputs (git-ignored, but they travel to the GPU box with the gpurun snapshot):
+    flashattention-from-scratch-with-triton_b200/libfa_sm100.so
+    build/fa_bringup
+nvcc cross-compiles for sm_100a without a GPU.  -lineinfo keeps the ncu source page usable.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libfa_sm100.so")
+BRINGUP = os.path.join(ROOT, "build", "fa_bringup")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "--use_fast_math"]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: libfa_sm100.so cannot be built (there is no non-CUDA fallback)")
+    return nvcc
+
+
+def _stale(target: str, srcs: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def _sources() -> list[str]:
+    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    out.append(os.path.join(ROOT, "include", "fa_sm100.h"))
+    return out
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale(LIB, _sources()):
+        return LIB
+    cmd = [_nvcc(), *ARCH, *COMMON, "-shared", "-Xcompiler", "-fPIC", "-o", LIB, os.path.join(CSRC, "fa_api.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libfa_sm100.so")
+    return LIB
+
+
+def build_bringup(force: bool = False) -> str:
+    os.makedirs(os.path.dirname(BRINGUP), exist_ok=True)
+    srcs = [os.path.join(CSRC, "fa_bringup.cu"), os.path.join(CSRC, "fa_ptx.cuh")]
+    if not force and not _stale(BRINGUP, srcs):
+        return BRINGUP
+    cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-o", BRINGUP, srcs[0]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building fa_bringup")
+    return BRINGUP
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--bringup", action="store_true")
+    ap.add_argument("-v", "--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build_lib(a.force, a.verbose))
+    if a.bringup:
+        print(build_bringup(a.force))

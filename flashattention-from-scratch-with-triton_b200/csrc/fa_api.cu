@@ -1,0 +1,219 @@
+// C-ABI entry points of libfa_sm100.so (declared in include/fa_sm100.h): argument checks, host-side
+// CUtensorMap construction (replaces the reference's TensorDescriptor objects and autotune
+// pre-hooks, code/My_FlashAttention_optimized.py:33-51 and kernel file :7-16), launches.
+#include "fa_fwd.cuh"
+#include "fa_bwd.cuh"
+#include "fa_aux.cuh"
+#include "../../include/fa_sm100.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+using namespace fa;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// [BH, S, D] 16-bit tensor viewed as a 3-D map (never flattened across heads, so a partial tile
+// cannot touch the next head — fixes the reference's flattened-descriptor overrun).
+// Box = [1][box_rows][64 columns], SWIZZLE_128B; out-of-range rows read as zero and are not written.
+bool make_map(CUtensorMap* m, const void* ptr, int BH, int S, int D, int dtype, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)BH};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)S * D * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, dtype == FA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                     3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+struct DeviceInfo { int sms = 0; int cc_major = 0; unsigned int* sched_ring = nullptr; };
+constexpr int kMaxDevices = 64;
+constexpr int kSchedRing = 1024;
+__device__ unsigned int g_sched_ring[kSchedRing];
+DeviceInfo g_dev[kMaxDevices];
+std::mutex g_dev_mu;
+std::atomic<unsigned int> g_sched_next{0};
+
+int device_info(DeviceInfo** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= kMaxDevices) return fail(FA_ERR_DEVICE, "device ordinal %d out of range", dev);
+    DeviceInfo& d = g_dev[dev];
+    if (d.sms == 0) {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        if (d.sms == 0) {
+            int sms = 0, major = 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+            void* ring = nullptr;
+            e = cudaGetSymbolAddress(&ring, g_sched_ring);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(sched ring) — was the library built for sm_100a?");
+            d.cc_major = major; d.sched_ring = (unsigned int*)ring; d.sms = sms;
+        }
+    }
+    if (d.cc_major != 10) return fail(FA_ERR_DEVICE, "libfa_sm100 needs compute capability 10.x, device has %d.x", d.cc_major);
+    *out = &d;
+    return 0;
+}
+
+int check_common(int B, int H, int Sq, int Sk, int D, int dtype) {
+    if (dtype != FA_DTYPE_FP16 && dtype != FA_DTYPE_BF16) return fail(FA_ERR_DTYPE, "dtype %d not in {0=fp16, 1=bf16}", dtype);
+    if (D != 64 && D != 128) return fail(FA_ERR_HEADDIM, "head dim %d not in {64, 128}", D);
+    if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return fail(FA_ERR_SHAPE, "non-positive dimension B=%d H=%d Sq=%d Sk=%d", B, H, Sq, Sk);
+    if ((long long)B * H > 2147483647LL / 4) return fail(FA_ERR_SHAPE, "B*H too large");
+    return 0;
+}
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename K> cudaError_t set_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+template <int D, bool kBf16>
+int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
+               const FwdParams& p, int grid, cudaStream_t st) {
+    static std::once_flag once; static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = set_smem(fa_fwd_kernel<D, kBf16>, FwdCfg<D>::kSmemBytes); });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(fwd smem)");
+    fa_fwd_kernel<D, kBf16><<<grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mo, p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd_kernel launch");
+}
+
+}  // namespace
+
+extern "C" {
+
+int fa_sm100_version(void) { return 100; }
+const char* fa_last_error(void) { return g_err; }
+unsigned long long fa_sm100_launch_count(void) { return g_launches.load(); }
+
+int fa_sm100_supported(int D, int dtype, int Sq, int Sk) {
+    return (D == 64 || D == 128) && (dtype == 0 || dtype == 1) && Sq > 0 && Sk > 0;
+}
+
+int fa_sm100_last_hang(unsigned int out[4]) {
+    unsigned int flag = 0;
+    if (cudaMemcpyFromSymbol(&flag, g_hang_flag, sizeof(flag)) != cudaSuccess || !flag) return 0;
+    HangRecord r;
+    if (cudaMemcpyFromSymbol(&r, g_hang_record, sizeof(r)) != cudaSuccess) return 0;
+    out[0] = r.tag; out[1] = r.block; out[2] = r.thread; out[3] = r.parity;
+    flag = 0;
+    cudaMemcpyToSymbol(g_hang_flag, &flag, sizeof(flag));     // re-arm
+    return 1;
+}
+
+int fa_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                 int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale, void* stream) {
+    if (!q || !k || !v || !o || !lse) return fail(FA_ERR_NULL, "null tensor pointer");
+    if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return fail(FA_ERR_ALIGN, "q/k/v/o must be 16-byte aligned");
+    DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
+    const int BH = B * H;
+    CUtensorMap mq, mk, mv, mo;
+    if (!make_map(&mq, q, BH, Sq, D, dtype, 128) || !make_map(&mk, k, BH, Sk, D, dtype, 128) ||
+        !make_map(&mv, v, BH, Sk, D, dtype, 128) || !make_map(&mo, o, BH, Sq, D, dtype, 128))
+        return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (BH=%d Sq=%d Sk=%d D=%d)", BH, Sq, Sk, D);
+    FwdParams p;
+    p.BH = BH; p.Sq = Sq; p.Sk = Sk;
+    p.n_qblk = (Sq + 255) / 256;
+    p.n_items = BH * p.n_qblk;
+    p.causal = causal ? 1 : 0;
+    p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
+    p.scale_log2 = p.scale * 1.44269504088896340736f;
+    p.lse = lse;
+    p.sched = dev->sched_ring + (g_sched_next.fetch_add(1) % kSchedRing);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(p.sched, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(sched)");
+    const int grid = p.n_items < dev->sms ? p.n_items : dev->sms;
+    if (D == 64) return dtype ? launch_fwd<64, true>(mq, mk, mv, mo, p, grid, st) : launch_fwd<64, false>(mq, mk, mv, mo, p, grid, st);
+    return dtype ? launch_fwd<128, true>(mq, mk, mv, mo, p, grid, st) : launch_fwd<128, false>(mq, mk, mv, mo, p, grid, st);
+}
+
+int fa_sm100_delta(const void* o, const void* dout, float* delta, int B, int H, int Sq, int D, int dtype, void* stream) {
+    if (!o || !dout || !delta) return fail(FA_ERR_NULL, "null tensor pointer");
+    if (int rc = check_common(B, H, Sq, 1, D, dtype)) return rc;
+    if (!aligned16(o) || !aligned16(dout)) return fail(FA_ERR_ALIGN, "o/dout must be 16-byte aligned");
+    DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
+    int rc = launch_delta(o, dout, delta, (long long)B * H * Sq, D, dtype, dev->sms, (cudaStream_t)stream);
+    ++g_launches;
+    return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_delta_kernel launch");
+}
+
+int fa_sm100_merge(float* o_acc, float* lse_acc, const void* o_part, const float* lse_part,
+                   int B, int H, int Sq, int D, int dtype, void* stream) {
+    if (!o_acc || !lse_acc || !o_part || !lse_part) return fail(FA_ERR_NULL, "null tensor pointer");
+    if (int rc = check_common(B, H, Sq, 1, D, dtype)) return rc;
+    DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
+    int rc = launch_merge(o_acc, lse_acc, o_part, lse_part, (long long)B * H * Sq, D, dtype, dev->sms, (cudaStream_t)stream);
+    ++g_launches;
+    return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_merge_kernel launch");
+}
+
+int fa_sm100_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                 const float* lse, void* dq, void* dk, void* dv, float* delta,
+                 int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale, void* stream) {
+    if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta) return fail(FA_ERR_NULL, "null tensor pointer");
+    if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dout) ||
+        !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || !aligned16(lse) || !aligned16(delta))
+        return fail(FA_ERR_ALIGN, "all tensors must be 16-byte aligned");
+    DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int BH = B * H;
+    int rc = launch_delta(o, dout, delta, (long long)BH * Sq, D, dtype, dev->sms, st);
+    ++g_launches;
+    if (rc) return cuda_fail((cudaError_t)rc, "fa_delta_kernel launch");
+    CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
+    if (!make_map(&mq, q, BH, Sq, D, dtype, 128) || !make_map(&mk, k, BH, Sk, D, dtype, 128) ||
+        !make_map(&mv, v, BH, Sk, D, dtype, 128) || !make_map(&mdo, dout, BH, Sq, D, dtype, 128) ||
+        !make_map(&mdq, dq, BH, Sq, D, dtype, 128) || !make_map(&mdk, dk, BH, Sk, D, dtype, 128) ||
+        !make_map(&mdv, dv, BH, Sk, D, dtype, 128))
+        return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (BH=%d Sq=%d Sk=%d D=%d)", BH, Sq, Sk, D);
+    BwdParams p;
+    p.BH = BH; p.Sq = Sq; p.Sk = Sk; p.causal = causal ? 1 : 0;
+    p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
+    p.scale_log2 = p.scale * 1.44269504088896340736f;
+    p.lse = lse; p.delta = delta;
+    p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
+    rc = launch_bwd(mq, mk, mv, mdo, mdq, mdk, mdv, p, D, dtype, st);
+    g_launches += 2;
+    return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_bwd kernels launch");
+}
+
+}  // extern "C"

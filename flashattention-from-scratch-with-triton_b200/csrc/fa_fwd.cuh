@@ -2,7 +2,7 @@
 // Replaces flash_attention_forward_kernel (reference code/_flash_attention_kernel_optimized.py:34-129)
 // with a persistent, warp-specialized tcgen05 / TMA kernel.
 //
-// CTA = 320 threads, one CTA per SM, each work item = 256 query rows of one (batch, head):
+// CTA = 384 threads (warps 10-11 idle; they donate registers via setmaxnreg), one CTA per SM, each work item = 256 query rows of one (batch, head):
 //   warps 0-3  softmax warpgroup for Q tile 0 (rows 0..127 of the item; thread r <-> TMEM lane r)
 //   warps 4-7  softmax warpgroup for Q tile 1
 //   warp  8    MMA issuer (one thread): S_t = Q_t K^T, O_t += P_t V on tcgen05, accumulators in TMEM
@@ -40,7 +40,8 @@ template <int D> struct FwdCfg {
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 64 + 1024;   // +1024: manual alignment slack
 };
 
-constexpr int kFwdThreads = 320;
+constexpr int kFwdThreads = 384;    // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
+constexpr int kFwdRegsSoftmax = 208, kFwdRegsOther = 80;   // setmaxnreg split of the 168 x 384 launch pool
 constexpr float kLazyRescaleLog2 = 8.0f;   // rescale O only when the row max grows by > 2^8 in exp2 units
 
 // iterations (128-wide K/V tiles) that tile `t` of the item starting at row q0 must visit
@@ -98,8 +99,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 9) {
+    if (warp >= 10) {
+        reg_dealloc<kFwdRegsOther>();     // idle warps (register donors)
+    } else if (warp == 9) {
         // ================================ TMA producer + scheduler ================================
+        reg_dealloc<kFwdRegsOther>();
         if (lane_id() == 0) {
             tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV);
             uint32_t kv_cnt = 0;        // K/V tiles produced so far
@@ -143,6 +147,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
     } else if (warp == 8) {
         // ======================================= MMA issuer =======================================
+        reg_dealloc<kFwdRegsOther>();
         if (lane_id() == 0) {
             constexpr uint32_t idesc_s = make_idesc(kBf16, false, false, 128, 128);
             constexpr uint32_t idesc_pv = make_idesc(kBf16, false, true, 128, D);
@@ -232,6 +237,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
     } else {
         // ================================= softmax warpgroups (0,1) ================================
+        reg_alloc<kFwdRegsSoftmax>();
         const int t = warp >> 2;                       // Q tile handled by this warpgroup
         const int r = tid & 127;                       // row inside the tile == TMEM lane
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;

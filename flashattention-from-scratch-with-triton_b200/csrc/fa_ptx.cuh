@@ -65,29 +65,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must never hang the GPU box.  After ~4 s without progress the
-// waiter records who it is and traps (the launch then fails with a CUDA error instead of hanging).
+// Bounded wait: a protocol bug must never hang the GPU box.  After ~4 s without progress the first
+// waiter records who it is and sets g_hang_flag; every waiter then abandons its wait, so the kernel
+// drains (with garbage results) and the host can read the record (fa_sm100_last_hang) instead of
+// facing a dead context.
 #ifndef FA_WAIT_TIMEOUT_NS
 #define FA_WAIT_TIMEOUT_NS 4000000000ull
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
-    if (mbar_try_wait(bar, parity)) return;
+__device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t tag) {
     uint64_t t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3fff) == 0) {
-            uint64_t now = globaltimer_ns();
+        if ((++spins & 0x3ff) == 0) {
+            if (*reinterpret_cast<volatile unsigned int*>(&g_hang_flag)) return;
+            const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > FA_WAIT_TIMEOUT_NS) {
                 if (atomicExch(&g_hang_flag, 1u) == 0u) {
                     g_hang_record.tag = tag; g_hang_record.block = blockIdx.x;
                     g_hang_record.thread = threadIdx.x; g_hang_record.parity = parity;
-                    __threadfence_system();
+                    __threadfence();
                 }
-                __trap();
+                return;
             }
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, tag);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -268,6 +274,10 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t c16) {
     return row * 128u + ((c16 ^ (row & 7u)) << 4);
 }
+
+// register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it)
+template <int N> __device__ __forceinline__ void reg_alloc()   { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
 
 // named barrier over a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

@@ -1,0 +1,88 @@
+/* C ABI of libfa_sm100.so — the drop-in boundary beneath the reference's Python operator.
+ *
+ * The reference has no FFI: its "plugin API" is the Python operator in
+ * /root/reference/code/My_FlashAttention_optimized.py and its device code is Triton JIT.
+ * Each entry point below replaces one reference launcher (file:line given per function); the
+ * Python mirror of the operator (flashattention-from-scratch-with-triton_b200/interface.py)
+ * binds them with ctypes.  INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *  - every pointer is a DEVICE pointer owned by the caller; nothing is retained after return
+ *  - tensors are contiguous [B, H, S, D] (D innermost), 16-byte aligned; K and V share B, H, D with Q
+ *  - dtype: 0 = fp16, 1 = bf16 (inputs, outputs and tensor-core operands); statistics are fp32
+ *  - work is enqueued on `stream` (a cudaStream_t) of the CURRENT device; no sync, no device allocation
+ *  - return 0 on success, < 0 = FA_ERR_* (argument rejected, nothing launched), > 0 = cudaError_t
+ *  - thread-safe; fa_last_error() is thread-local
+ *  - there is no CPU fallback and no alternative backend: unsupported arguments are an error
+ */
+#ifndef FA_SM100_H_
+#define FA_SM100_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_OK 0
+#define FA_ERR_NULL (-1)      /* a required pointer is NULL */
+#define FA_ERR_DTYPE (-2)     /* dtype not in {0, 1} */
+#define FA_ERR_HEADDIM (-3)   /* D not in {64, 128} */
+#define FA_ERR_SHAPE (-4)     /* non-positive dimension or a size the tensor maps cannot encode */
+#define FA_ERR_ALIGN (-5)     /* a base pointer is not 16-byte aligned */
+#define FA_ERR_DRIVER (-6)    /* cuTensorMapEncodeTiled unavailable or failed */
+#define FA_ERR_DEVICE (-7)    /* current device is not compute capability 10.x */
+
+#define FA_DTYPE_FP16 0
+#define FA_DTYPE_BF16 1
+
+/* Forward.  Replaces flash_attention_forward + flash_attention_forward_kernel
+ * (code/My_FlashAttention_optimized.py:14-60, code/_flash_attention_kernel_optimized.py:34-129).
+ *   o   [B,H,Sq,D] dtype      = softmax(q k^T * sm_scale [+ causal mask]) v
+ *   lse [B,H,Sq]   fp32       = max + ln(sum exp) of the scaled, masked scores (natural log)
+ * causal != 0: top-left aligned mask, row i attends to columns <= i (kernel :102).
+ * sm_scale <= 0 selects the reference's hard-wired 1/sqrt(D) (launcher :56). */
+int fa_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                 int B, int H, int Sq, int Sk, int D, int dtype, int causal,
+                 float sm_scale, void* stream);
+
+/* Backward.  Replaces flash_attention_backward + the dQ and dKV kernels
+ * (code/My_FlashAttention_optimized.py:62-128, code/_flash_attention_kernel_optimized.py:164-386).
+ *   delta [B,H,Sq] fp32 is caller-provided scratch; on return it holds rowsum(dout * o)
+ *   (the reference's dQ kernel writes the same tensor, kernel :210-211, :258).
+ *   dq [B,H,Sq,D], dk, dv [B,H,Sk,D] in dtype.  Deterministic (no atomics). */
+int fa_sm100_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                 const float* lse, void* dq, void* dk, void* dv, float* delta,
+                 int B, int H, int Sq, int Sk, int D, int dtype, int causal,
+                 float sm_scale, void* stream);
+
+/* delta = rowsum(dout * o) alone (the preprocess step of the backward; kernel :210-211). */
+int fa_sm100_delta(const void* o, const void* dout, float* delta,
+                   int B, int H, int Sq, int D, int dtype, void* stream);
+
+/* Ring / partial attention support (no reference counterpart):
+ * in-place merge of a partial result (o_part, lse_part) over a disjoint key set into the running
+ * (o_acc fp32 [B,H,Sq,D], lse_acc fp32 [B,H,Sq]):
+ *   lse = logaddexp(lse_acc, lse_part);  o_acc = o_acc*e^(lse_acc-lse) + o_part*e^(lse_part-lse).
+ * lse = -inf partials are the identity. */
+int fa_sm100_merge(float* o_acc, float* lse_acc, const void* o_part, const float* lse_part,
+                   int B, int H, int Sq, int D, int dtype, void* stream);
+
+/* Capability query, no launch: 1 if fa_sm100_fwd/bwd accept (D, dtype, Sq, Sk), else 0. */
+int fa_sm100_supported(int D, int dtype, int Sq, int Sk);
+
+/* Thread-local message for the last non-zero return of this thread ("" if none). */
+const char* fa_last_error(void);
+
+/* Library/ABI version (major*100 + minor). */
+int fa_sm100_version(void);
+
+/* Number of this library's kernels launched by the calling process so far (bench bookkeeping). */
+unsigned long long fa_sm100_launch_count(void);
+
+/* Debug: if a kernel aborted on a pipeline time-out, copies {tag, block, thread, parity} of the
+ * first waiter that gave up into out[4] and returns 1; returns 0 if no time-out was recorded. */
+int fa_sm100_last_hang(unsigned int out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_SM100_H_ */
