@@ -1,8 +1,529 @@
-// placeholder until the backward kernels land
+// Backward attention for sm_100a.  Replaces flash_attention_dQ_kernel and flash_attention_dKV_kernel
+// (reference code/_flash_attention_kernel_optimized.py:164-258 and :291-386); delta comes from the
+// preprocess kernel in fa_aux.cuh.  Same two-kernel, atomic-free (deterministic) structure as the
+// reference; both kernels recompute P from the saved LSE.
+//
+// Common CTA shape: 384 threads
+//   warps 0-3  compute warpgroup A : TMEM lane r = tid & 127, columns [0,64) of the 128-wide score tile
+//   warps 4-7  compute warpgroup B : same lanes, columns [64,128)
+//   warp  8    MMA issuer (one thread)      warp 9  TMA producer (one thread)
+//   warp  10   statistics loader (dKV only: per-column -LSE*log2e and delta -> smem)   warp 11 idle
+//
+// dKV kernel (one CTA per 128-row K/V tile, loops over Q tiles i), transposed so kv rows are lanes:
+//   S^T = K Q_i^T, dP^T = V dO_i^T  (SS MMAs, N = 128)        TMEM: S^T [0,128) dP^T [128,256)
+//   P^T = exp2(S^T c - LSE_i log2e) -> 16-bit over S^T; dV += P^T dO_i    (A from TMEM, B = dO_i MN-major)
+//   dS^T = P^T o (dP^T - delta_i)   -> 16-bit over dP^T; dK += dS^T Q_i   TMEM: dV [256,256+D) dK [256+D,..)
+// dQ kernel (one CTA per 128-row Q tile, loops over K/V tiles j):
+//   S = Q K_j^T, dP = dO V_j^T; dS = P o (dP - delta) -> 16-bit over dP; dQ += dS K_j (B = K_j MN-major)
+//   TMEM: S [0,128) dP [128,256) dQ [256,256+D).  S is released as soon as it is in registers, so
+//   S(j+1) runs under the exp/dS math of tile j.
+// Each warpgroup packs its 64 columns into the first 32 TMEM columns of ITS OWN half of the region
+// it overwrites, so the two warpgroups never touch each other's unread data; the MMA issuer
+// addresses the two 32-column runs explicitly per K=16 step.
 #pragma once
 #include "fa_ptx.cuh"
+#include "fa_fwd.cuh"   // fwd_tile_iters
+
 namespace fa {
-struct BwdParams { int BH, Sq, Sk, causal; float scale, scale_log2; const float* lse; const float* delta; int n_qtiles, n_ktiles; };
-inline int launch_bwd(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                      const CUtensorMap&, const CUtensorMap&, const BwdParams&, int, int, cudaStream_t) { return (int)cudaErrorNotSupported; }
+
+struct BwdParams {
+    int BH, Sq, Sk, causal;
+    float scale, scale_log2;
+    const float* lse;      // [BH, Sq]
+    const float* delta;    // [BH, Sq]
+    int n_qtiles, n_ktiles;
+};
+
+constexpr int kBwdThreads = 384;
+constexpr int kBwdRegsCompute = 208, kBwdRegsOther = 80;
+constexpr float kLog2e = 1.44269504088896340736f;
+
+template <int D> struct BwdCfg {
+    static constexpr int kChunks = D / 64;
+    static constexpr int kTileBytes = 128 * D * 2;
+    static constexpr int kStages = (D == 128) ? 2 : 4;
+    // resident pair (K,V for dKV; Q,dO for dQ) + kStages x streamed pair (+ 1 KB statistics per stage)
+    static constexpr int kOffRes = 0;
+    static constexpr int kOffStage = 2 * kTileBytes;
+    static constexpr int kStageBytes = 2 * kTileBytes;
+    static constexpr int kOffStat = kOffStage + kStages * kStageBytes;
+    static constexpr int kOffBar = kOffStat + kStages * 1024;
+    static constexpr int kNumBars = 4 + 5 * kStages + 8;
+    static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+};
+
+// score-tile MMA: D[tmem 128x128] = A[smem 128 x D, K-major] * B[smem 128 x D, K-major]^T
+template <int D, bool kBf16>
+__device__ __forceinline__ void issue_scores(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr) {
+    constexpr uint32_t idesc = make_idesc(kBf16, false, false, 128, 128);
+    #pragma unroll
+    for (int k = 0; k < D / 16; ++k) {
+        const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+        umma_ss(d_tmem, make_smem_desc(a_addr + off, 0, 1024), make_smem_desc(b_addr + off, 0, 1024), idesc, k > 0);
+    }
 }
+// gradient MMA: D[tmem 128 x D] (+)= A[tmem: 128 lanes x 128 16-bit, two 32-column runs at a_tmem and
+// a_tmem+64] * B[smem 128 rows x D, MN-major]
+template <int D, bool kBf16>
+__device__ __forceinline__ void issue_grad(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, bool acc) {
+    constexpr uint32_t idesc = make_idesc(kBf16, false, true, 128, D);
+    #pragma unroll
+    for (int k = 0; k < 8; ++k)
+        umma_ts(d_tmem, a_tmem + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc(b_addr + k * 2048, 16384, 1024),
+                idesc, acc || k > 0);
+}
+
+// TMEM accumulator half-row (D/2 columns starting at h*D/2) -> scaled 16-bit -> SWIZZLE_128B staging tile
+template <int D, bool kBf16>
+__device__ __forceinline__ void stage_grad_half(uint32_t t_acc, uint8_t* stage, int r, int h, float mul, bool zero) {
+    constexpr int kCols = D / 2;
+    #pragma unroll
+    for (int q = 0; q < kCols / 32; ++q) {
+        uint32_t v[32];
+        if (!zero) { tmem_ld32(t_acc + h * kCols + q * 32, v); tc_wait_ld(); }
+        else {
+            #pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        const int col0 = h * kCols + q * 32;             // first of 32 columns held in v
+        uint8_t* chunk = stage + (col0 >> 6) * 16384;
+        #pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+                w[i] = pack2<kBf16>(__uint_as_float(v[g * 8 + 2 * i]) * mul, __uint_as_float(v[g * 8 + 2 * i + 1]) * mul);
+            *reinterpret_cast<uint4*>(chunk + sw128_offset(r, ((col0 & 63) >> 3) + g)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+// =================================================================================================
+// dK / dV
+// =================================================================================================
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                  const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
+                  const __grid_constant__ CUtensorMap mapdK, const __grid_constant__ CUtensorMap mapdV,
+                  const BwdParams p) {
+    using C = BwdCfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem + C::kOffRes;
+    uint8_t* sV = sK + C::kTileBytes;
+    uint8_t* sStage = smem + C::kOffStage;             // per stage: Q_i then dO_i
+    float* sStat = reinterpret_cast<float*>(smem + C::kOffStat);   // per stage: 128 x nlse2, 128 x delta
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+    uint64_t* k_full = bars;            uint64_t* v_full = bars + 1;
+    uint64_t* s_full = bars + 2;        uint64_t* dp_full = bars + 3;
+    uint64_t* p_full = bars + 4;        uint64_t* ds_full = bars + 5;
+    uint64_t* acc_full = bars + 6;
+    uint64_t* q_full = bars + 8;                        // [kStages]
+    uint64_t* do_full = q_full + C::kStages;            // [kStages]
+    uint64_t* stat_full = do_full + C::kStages;         // [kStages]
+    uint64_t* stage_empty = stat_full + C::kStages;     // [kStages]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.x / p.n_ktiles;
+    const int jt = blockIdx.x % p.n_ktiles;            // ascending kv tile = heavy first under causal
+    const int i_start = p.causal ? jt : 0;             // first Q tile with a row >= kv_block_start (:341)
+    const int n_it = max(p.n_qtiles - i_start, 0);
+
+    if (tid == 0) {
+        mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1);
+        mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1);
+        for (int i = 0; i < C::kStages; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&do_full[i], 1); mbar_init(&stat_full[i], 1);
+            mbar_init(&stage_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 256 + D;
+
+    if (warp == 11) {
+        reg_dealloc<kBwdRegsOther>();
+    } else if (warp == 10) {
+        // ------------------------------ statistics loader ------------------------------
+        reg_dealloc<kBwdRegsOther>();
+        const int lane = lane_id();
+        for (int it = 0; it < n_it; ++it) {
+            const int st = it % C::kStages;
+            mbar_wait(&stage_empty[st], ((it / C::kStages) & 1) ^ 1, 400);
+            const int q0 = (i_start + it) * 128;
+            float* dst = sStat + st * 256;
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = lane + u * 32, row = q0 + c;
+                float nl = -INFINITY, dl = 0.f;          // out-of-range query rows: P = exp2(-inf) = 0
+                if (row < p.Sq) {
+                    const float l = p.lse[(size_t)bh * p.Sq + row];
+                    nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+                    dl = p.delta[(size_t)bh * p.Sq + row];
+                }
+                dst[c] = nl; dst[128 + c] = dl;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stat_full[st]);
+        }
+    } else if (warp == 9) {
+        // --------------------------------- TMA producer ---------------------------------
+        reg_dealloc<kBwdRegsOther>();
+        if (lane_id() == 0 && n_it > 0) {
+            tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO);
+            mbar_arrive_expect_tx(k_full, C::kTileBytes);
+            #pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sK + c * 16384, &mapK, k_full, c * 64, jt * 128, bh);
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it % C::kStages;
+                uint8_t* sQi = sStage + st * C::kStageBytes;
+                uint8_t* sdOi = sQi + C::kTileBytes;
+                const int q0 = (i_start + it) * 128;
+                mbar_wait(&stage_empty[st], ((it / C::kStages) & 1) ^ 1, 410);
+                mbar_arrive_expect_tx(&q_full[st], C::kTileBytes);
+                #pragma unroll
+                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sQi + c * 16384, &mapQ, &q_full[st], c * 64, q0, bh);
+                if (it == 0) {
+                    mbar_arrive_expect_tx(v_full, C::kTileBytes);
+                    #pragma unroll
+                    for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sV + c * 16384, &mapV, v_full, c * 64, jt * 128, bh);
+                }
+                mbar_arrive_expect_tx(&do_full[st], C::kTileBytes);
+                #pragma unroll
+                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sdOi + c * 16384, &mapdO, &do_full[st], c * 64, q0, bh);
+            }
+        }
+    } else if (warp == 8) {
+        // ---------------------------------- MMA issuer ----------------------------------
+        reg_dealloc<kBwdRegsOther>();
+        if (lane_id() == 0 && n_it > 0) {
+            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aSt = smem_u32(sStage);
+            mbar_wait(k_full, 0, 420);
+            mbar_wait(&q_full[0], 0, 421); tc_fence_after();
+            issue_scores<D, kBf16>(tmem + kColST, aK, aSt); tc_commit(s_full);
+            mbar_wait(v_full, 0, 422);
+            mbar_wait(&do_full[0], 0, 423); tc_fence_after();
+            issue_scores<D, kBf16>(tmem + kColDPT, aV, aSt + C::kTileBytes); tc_commit(dp_full);
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it % C::kStages;
+                const uint32_t aQ = aSt + st * C::kStageBytes, adO = aQ + C::kTileBytes;
+                const bool more = it + 1 < n_it;
+                const int st1 = (it + 1) % C::kStages;
+                const uint32_t ph1 = ((it + 1) / C::kStages) & 1;
+                const uint32_t aQ1 = aSt + st1 * C::kStageBytes;
+                mbar_wait(p_full, it & 1, 424); tc_fence_after();
+                issue_grad<D, kBf16>(tmem + kColDV, tmem + kColST, adO, it > 0);          // dV += P^T dO_i
+                if (more) {
+                    mbar_wait(&q_full[st1], ph1, 425); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColST, aK, aQ1); tc_commit(s_full);     // S^T(i+1)
+                }
+                mbar_wait(ds_full, it & 1, 426); tc_fence_after();
+                issue_grad<D, kBf16>(tmem + kColDK, tmem + kColDPT, aQ, it > 0);           // dK += dS^T Q_i
+                tc_commit(&stage_empty[st]);
+                if (more) {
+                    mbar_wait(&do_full[st1], ph1, 427); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColDPT, aV, aQ1 + C::kTileBytes); tc_commit(dp_full);   // dP^T(i+1)
+                }
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        // ------------------------------- compute warpgroups -------------------------------
+        reg_alloc<kBwdRegsCompute>();
+        const int h = warp >> 2;                         // column half
+        const int r = tid & 127;                         // kv row in tile == TMEM lane
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tST = tmem + lane_field + kColST + h * 64;
+        const uint32_t tDPT = tmem + lane_field + kColDPT + h * 64;
+        const int kv_g = jt * 128 + r;
+        const float c2 = p.scale_log2;
+        for (int it = 0; it < n_it; ++it) {
+            const int st = it % C::kStages;
+            const float* stat = sStat + st * 256 + h * 64;
+            const int q0 = (i_start + it) * 128 + h * 64;       // global query index of my column 0
+            mbar_wait(&stat_full[st], (it / C::kStages) & 1, 430);
+            mbar_wait(s_full, it & 1, 431);
+            tc_fence_after();
+            float pv[64];
+            {
+                uint32_t s[2][32];
+                tmem_ld32(tST, s[0]); tmem_ld32(tST + 32, s[1]);
+                tc_wait_ld();
+                #pragma unroll
+                for (int c = 0; c < 64; c += 4) {
+                    const float4 nl = *reinterpret_cast<const float4*>(stat + c);
+                    pv[c]     = ex2_approx(fmaf(__uint_as_float(s[c >> 5][c & 31]),             c2, nl.x));
+                    pv[c + 1] = ex2_approx(fmaf(__uint_as_float(s[(c + 1) >> 5][(c + 1) & 31]), c2, nl.y));
+                    pv[c + 2] = ex2_approx(fmaf(__uint_as_float(s[(c + 2) >> 5][(c + 2) & 31]), c2, nl.z));
+                    pv[c + 3] = ex2_approx(fmaf(__uint_as_float(s[(c + 3) >> 5][(c + 3) & 31]), c2, nl.w));
+                }
+            }
+            if (p.causal && q0 < kv_g) {                 // tile straddles the diagonal: keep q >= kv only
+                const int cmin = kv_g - q0;
+                #pragma unroll
+                for (int c = 0; c < 64; ++c) if (c < cmin) pv[c] = 0.f;
+            }
+            #pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t pk[16];
+                #pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = pack2<kBf16>(pv[q * 32 + 2 * i], pv[q * 32 + 2 * i + 1]);
+                tmem_st16(tST + q * 16, pk);
+            }
+            tc_wait_st(); tc_fence_before();
+            mbar_arrive(p_full);
+            mbar_wait(dp_full, it & 1, 432);
+            tc_fence_after();
+            {
+                uint32_t dp[2][32];
+                tmem_ld32(tDPT, dp[0]); tmem_ld32(tDPT + 32, dp[1]);
+                tc_wait_ld();
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t pk[16];
+                    #pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const int c = q * 32 + 2 * i;
+                        const float4 dl = *reinterpret_cast<const float4*>(stat + 128 + c);
+                        const float d0 = pv[c] * (__uint_as_float(dp[q][2 * i]) - dl.x);
+                        const float d1 = pv[c + 1] * (__uint_as_float(dp[q][2 * i + 1]) - dl.y);
+                        const float d2 = pv[c + 2] * (__uint_as_float(dp[q][2 * i + 2]) - dl.z);
+                        const float d3 = pv[c + 3] * (__uint_as_float(dp[q][2 * i + 3]) - dl.w);
+                        pk[i] = pack2<kBf16>(d0, d1); pk[i + 1] = pack2<kBf16>(d2, d3);
+                    }
+                    tmem_st16(tDPT + q * 16, pk);
+                }
+            }
+            tc_wait_st(); tc_fence_before();
+            mbar_arrive(ds_full);
+        }
+        // epilogue: dV, dK*scale -> 16-bit -> smem (over V, K) -> TMA store
+        if (n_it > 0) { mbar_wait(acc_full, 0, 433); tc_fence_after(); }
+        stage_grad_half<D, kBf16>(tmem + lane_field + kColDV, sV, r, h, 1.0f, n_it == 0);
+        stage_grad_half<D, kBf16>(tmem + lane_field + kColDK, sK, r, h, p.scale, n_it == 0);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        if (tid == 0) {
+            #pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) {
+                tma_store_3d(&mapdV, sV + c * 16384, c * 64, jt * 128, bh);
+                tma_store_3d(&mapdK, sK + c * 16384, c * 64, jt * 128, bh);
+            }
+            tma_store_commit();
+            tma_store_wait_all0();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// =================================================================================================
+// dQ
+// =================================================================================================
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
+                 const __grid_constant__ CUtensorMap mapdQ, const BwdParams p) {
+    using C = BwdCfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + C::kOffRes;
+    uint8_t* sdO = sQ + C::kTileBytes;
+    uint8_t* sStage = smem + C::kOffStage;             // per stage: K_j then V_j
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+    uint64_t* q_full = bars;            uint64_t* do_full = bars + 1;
+    uint64_t* s_full = bars + 2;        uint64_t* dp_full = bars + 3;
+    uint64_t* s_empty = bars + 4;       uint64_t* ds_full = bars + 5;
+    uint64_t* acc_full = bars + 6;
+    uint64_t* k_full = bars + 8;                        // [kStages]
+    uint64_t* v_full = k_full + C::kStages;             // [kStages]
+    uint64_t* stage_empty = v_full + C::kStages;        // [kStages]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.x / p.n_qtiles;
+    const int iq = p.n_qtiles - 1 - (blockIdx.x % p.n_qtiles);      // descending q tile = heavy first under causal
+    const int n_it = fwd_tile_iters(iq * 128, 0, p.Sq, p.Sk, p.causal);   // same truncation as forward (:219)
+
+    if (tid == 0) {
+        mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1);
+        mbar_init(s_empty, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1);
+        for (int i = 0; i < C::kStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&stage_empty[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256;
+
+    if (warp >= 10) {
+        reg_dealloc<kBwdRegsOther>();
+    } else if (warp == 9) {
+        reg_dealloc<kBwdRegsOther>();
+        if (lane_id() == 0) {
+            tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO);
+            mbar_arrive_expect_tx(q_full, C::kTileBytes);
+            #pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh);
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it % C::kStages;
+                uint8_t* sKj = sStage + st * C::kStageBytes;
+                uint8_t* sVj = sKj + C::kTileBytes;
+                mbar_wait(&stage_empty[st], ((it / C::kStages) & 1) ^ 1, 510);
+                mbar_arrive_expect_tx(&k_full[st], C::kTileBytes);
+                #pragma unroll
+                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sKj + c * 16384, &mapK, &k_full[st], c * 64, it * 128, bh);
+                if (it == 0) {
+                    mbar_arrive_expect_tx(do_full, C::kTileBytes);
+                    #pragma unroll
+                    for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sdO + c * 16384, &mapdO, do_full, c * 64, iq * 128, bh);
+                }
+                mbar_arrive_expect_tx(&v_full[st], C::kTileBytes);
+                #pragma unroll
+                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sVj + c * 16384, &mapV, &v_full[st], c * 64, it * 128, bh);
+            }
+        }
+    } else if (warp == 8) {
+        reg_dealloc<kBwdRegsOther>();
+        if (lane_id() == 0) {
+            const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aSt = smem_u32(sStage);
+            mbar_wait(q_full, 0, 520);
+            mbar_wait(&k_full[0], 0, 521); tc_fence_after();
+            issue_scores<D, kBf16>(tmem + kColS, aQ, aSt); tc_commit(s_full);
+            mbar_wait(do_full, 0, 522);
+            mbar_wait(&v_full[0], 0, 523); tc_fence_after();
+            issue_scores<D, kBf16>(tmem + kColDP, adO, aSt + C::kTileBytes); tc_commit(dp_full);
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it % C::kStages;
+                const uint32_t aK = aSt + st * C::kStageBytes;
+                const bool more = it + 1 < n_it;
+                const int st1 = (it + 1) % C::kStages;
+                const uint32_t ph1 = ((it + 1) / C::kStages) & 1;
+                const uint32_t aK1 = aSt + st1 * C::kStageBytes;
+                if (more) {
+                    mbar_wait(s_empty, it & 1, 524);               // S(it) is in registers
+                    mbar_wait(&k_full[st1], ph1, 525); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColS, aQ, aK1); tc_commit(s_full);          // S(j+1)
+                }
+                mbar_wait(ds_full, it & 1, 526); tc_fence_after();
+                issue_grad<D, kBf16>(tmem + kColDQ, tmem + kColDP, aK, it > 0);                // dQ += dS K_j
+                tc_commit(&stage_empty[st]);
+                if (more) {
+                    mbar_wait(&v_full[st1], ph1, 527); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColDP, adO, aK1 + C::kTileBytes); tc_commit(dp_full);   // dP(j+1)
+                }
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        reg_alloc<kBwdRegsCompute>();
+        const int h = warp >> 2;
+        const int r = tid & 127;
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem + lane_field + kColS + h * 64;
+        const uint32_t tDP = tmem + lane_field + kColDP + h * 64;
+        const int row_g = iq * 128 + r;
+        const float c2 = p.scale_log2;
+        float nl = -INFINITY, dl = 0.f;
+        if (row_g < p.Sq) {
+            const float l = p.lse[(size_t)bh * p.Sq + row_g];
+            nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+            dl = p.delta[(size_t)bh * p.Sq + row_g];
+        }
+        for (int it = 0; it < n_it; ++it) {
+            mbar_wait(s_full, it & 1, 530);
+            tc_fence_after();
+            float pv[64];
+            {
+                uint32_t s[2][32];
+                tmem_ld32(tS, s[0]); tmem_ld32(tS + 32, s[1]);
+                tc_wait_ld();
+                tc_fence_before();
+                mbar_arrive(s_empty);
+                #pragma unroll
+                for (int c = 0; c < 64; ++c) pv[c] = ex2_approx(fmaf(__uint_as_float(s[c >> 5][c & 31]), c2, nl));
+            }
+            const int k0 = it * 128 + h * 64;             // global key index of my column 0
+            int cmax = p.Sk - 1 - k0;
+            if (p.causal) cmax = min(cmax, row_g - k0);
+            if (cmax < 63) {
+                #pragma unroll
+                for (int c = 0; c < 64; ++c) if (c > cmax) pv[c] = 0.f;
+            }
+            mbar_wait(dp_full, it & 1, 531);
+            tc_fence_after();
+            {
+                uint32_t dp[2][32];
+                tmem_ld32(tDP, dp[0]); tmem_ld32(tDP + 32, dp[1]);
+                tc_wait_ld();
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t pk[16];
+                    #pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = q * 32 + 2 * i;
+                        pk[i] = pack2<kBf16>(pv[c] * (__uint_as_float(dp[q][2 * i]) - dl),
+                                             pv[c + 1] * (__uint_as_float(dp[q][2 * i + 1]) - dl));
+                    }
+                    tmem_st16(tDP + q * 16, pk);
+                }
+            }
+            tc_wait_st(); tc_fence_before();
+            mbar_arrive(ds_full);
+        }
+        mbar_wait(acc_full, 0, 532); tc_fence_after();
+        stage_grad_half<D, kBf16>(tmem + lane_field + kColDQ, sQ, r, h, p.scale, false);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        if (tid == 0) {
+            #pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) tma_store_3d(&mapdQ, sQ + c * 16384, c * 64, iq * 128, bh);
+            tma_store_commit();
+            tma_store_wait_all0();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+template <int D, bool kBf16>
+int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
+                 const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
+                 cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(fa_bwd_dkv_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<D>::kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(fa_bwd_dq_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<D>::kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    // same order as the reference launcher (code/My_FlashAttention_optimized.py:111-126): dQ, then dK/dV
+    fa_bwd_dq_kernel<D, kBf16><<<p.BH * p.n_qtiles, kBwdThreads, BwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    fa_bwd_dkv_kernel<D, kBf16><<<p.BH * p.n_ktiles, kBwdThreads, BwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
+    return (int)cudaGetLastError();
+}
+
+inline int launch_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
+                      const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
+                      int D, int dtype, cudaStream_t st) {
+    if (D == 64) return dtype ? launch_bwd_t<64, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, st)
+                              : launch_bwd_t<64, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, st);
+    return dtype ? launch_bwd_t<128, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, st)
+                 : launch_bwd_t<128, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, st);
+}
+
+}  // namespace fa

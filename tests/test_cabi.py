@@ -1,0 +1,86 @@
+"""The C-ABI library loads, exports every symbol include/fa_sm100.h declares, and rejects bad
+arguments with the documented codes — all without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fa_sm100.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    d = _declared()
+    for name in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_delta", "fa_sm100_merge", "fa_sm100_supported",
+                 "fa_last_error", "fa_sm100_version", "fa_sm100_launch_count", "fa_sm100_last_hang"):
+        assert name in d
+
+
+def test_library_exports_every_declared_symbol(lib):
+    import flashattn_b200._cabi as cabi
+    assert sorted(cabi.SYMBOLS) == _declared()
+    for name in _declared():
+        assert getattr(lib, name) is not None
+    assert lib.fa_sm100_version() >= 100
+
+
+def test_supported_query(lib):
+    assert lib.fa_sm100_supported(64, 0, 128, 128) == 1
+    assert lib.fa_sm100_supported(128, 1, 131072, 131072) == 1
+    assert lib.fa_sm100_supported(96, 1, 128, 128) == 0
+    assert lib.fa_sm100_supported(64, 2, 128, 128) == 0
+    assert lib.fa_sm100_supported(64, 1, 0, 128) == 0
+
+
+def test_argument_validation_without_gpu(lib):
+    p = 0x10000     # fake, aligned, never dereferenced: validation happens before any CUDA call
+    fwd = lambda q=p, D=64, dt=1, Sq=128, Sk=128, B=1: lib.fa_sm100_fwd(q, p, p, p, p, B, 2, Sq, Sk, D, dt, 0, 0.0, None)
+    assert fwd(q=None) == -1 and b"null" in lib.fa_last_error()
+    assert fwd(dt=3) == -2
+    assert fwd(D=96) == -3 and b"head dim" in lib.fa_last_error()
+    assert fwd(Sq=0) == -4
+    assert fwd(B=-1) == -4
+    assert fwd(q=p + 2) == -5
+    bwd = lambda dq=p, D=128, dt=0: lib.fa_sm100_bwd(p, p, p, p, p, p, dq, p, p, p, 1, 1, 128, 128, D, dt, 1, 0.0, None)
+    assert bwd(dq=None) == -1
+    assert bwd(D=32) == -3
+    assert bwd(dt=-1) == -2
+    assert bwd(dq=p + 8) == -5
+    assert lib.fa_sm100_delta(p, None, p, 1, 1, 128, 64, 1, None) == -1
+    assert lib.fa_sm100_merge(p, p, p, None, 1, 1, 128, 64, 1, None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    import flashattn_b200._cabi as cabi
+    monkeypatch.setattr(cabi, "_lib", None)
+    monkeypatch.setattr(cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError, match="no CPU or Triton fallback"):
+        cabi.load()
+
+
+def test_operator_asserts_like_the_reference():
+    """reference code/My_FlashAttention_optimized.py:133-136 — AssertionError, not a fallback."""
+    import torch
+    import flashattn_b200 as fa
+    q = torch.randn(1, 1, 128, 64, dtype=torch.float16)
+    with pytest.raises(AssertionError):
+        fa.flash_attention(q, q, q)                              # CPU tensors
+    with pytest.raises(AssertionError):
+        fa.FlashAttentionFunction.apply(q.float(), q.float(), q.float(), False)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, open or link it."""
+    pkg = os.path.join(ROOT, "flashattention-from-scratch-with-triton_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[/.]attention_oracle|oracle/_ref", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f

@@ -1,0 +1,87 @@
+"""The CPU oracle, pinned: against golden vectors produced by the reference's own Triton kernels
+(tests/golden/make_golden.py) and against independent restatements of the same math."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention_oracle as orc
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    meta = {k[5:]: z[k].item() for k in z.files if k.startswith("meta_")}
+    arrs = {k: torch.from_numpy(z[k]).float() for k in z.files if not k.startswith("meta_")}
+    return meta, arrs
+
+
+def test_golden_fixtures_present():
+    assert len(GOLD) >= 6
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_oracle_matches_reference_kernels(path):
+    """Blocked restatement == reference Triton kernels (CPU interpreter) to <= 2 fp16 ulp."""
+    m, g = _load(path)
+    dt = getattr(torch, m["dtype"])
+    Q, K, V, dO = orc.make_inputs(m["B"], m["H"], m["Sq"], m["Sk"], m["D"], dt, m["seed"])
+    causal = bool(m["causal"])
+    O, LSE = orc.forward_blocked(Q, K, V, causal, m["BLOCK_M"], m["BLOCK_N"])
+    dQ, dK, dV, delta = orc.backward_blocked(Q, K, V, O, dO, LSE, causal, m["BLOCK_M"], m["BLOCK_N"])
+    assert (LSE - g["LSE"]).abs().max() < 5e-6
+    for name, x in (("O", O), ("dQ", dQ), ("dK", dK), ("dV", dV)):
+        ref = g[name]
+        ulp = torch.clamp(ref.abs(), min=2.0 ** -10) * 2.0 ** -10      # fp16 ulp at that magnitude (approx.)
+        assert ((x.float() - ref).abs() <= 2.5 * ulp).all(), name
+    assert (delta - g["delta"]).abs().max() < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("D", [64, 128])
+def test_blocked_vs_closed_form_and_sdpa(dtype, causal, D):
+    Q, K, V, dO = orc.make_inputs(1, 2, 192, 192, D, dtype, seed=11)
+    O, LSE = orc.forward_blocked(Q, K, V, causal)
+    dQ, dK, dV, _ = orc.backward_blocked(Q, K, V, O, dO, LSE, causal)
+    cO, cLSE, cdQ, cdK, cdV = orc.closed_form(Q, K, V, dO, causal)
+    sO, sdQ, sdK, sdV = orc.sdpa_fp32(Q, K, V, dO, causal)
+    # the two ground truths agree to fp32 round-off
+    for a, b in ((cO, sO), (cdQ, sdQ), (cdK, sdK), (cdV, sdV)):
+        assert (a.float() - b).abs().max() < 2e-5
+    assert (LSE - cLSE.float()).abs().max() < 1e-3                    # Phase_3.md:752-753
+    assert (orc.lse_bench(Q, K, causal) - cLSE.float()).abs().max() < 1e-5
+    for a, b in ((O, cO), (dQ, cdQ), (dK, cdK), (dV, cdV)):            # BASELINE contract atol=rtol=1e-2
+        assert torch.allclose(a.float(), b.float(), rtol=1e-2, atol=1e-2)
+
+
+def test_block_size_independence():
+    Q, K, V, dO = orc.make_inputs(1, 1, 256, 256, 64, torch.float16, seed=3)
+    O1, L1 = orc.forward_blocked(Q, K, V, True, 64, 64)
+    O2, L2 = orc.forward_blocked(Q, K, V, True, 128, 128)
+    assert (L1 - L2).abs().max() < 1e-5
+    assert (O1.float() - O2.float()).abs().max() < 2e-3
+
+
+def test_cpu_flash_lse_matches():
+    Q, K, V = orc.make_inputs(1, 2, 128, 128, 64, torch.float32, seed=5, with_dO=False)
+    _, lse = orc.sdpa_cpu_flash(Q, K, V, None, True)
+    assert (lse - orc.lse_bench(Q, K, True)).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_merge_partials_is_attention_over_union(causal):
+    """(O, LSE) merge over two disjoint key blocks == attention over all keys (ring algebra)."""
+    Q, K, V = orc.make_inputs(1, 2, 128, 256, 64, torch.float32, seed=9, with_dO=False)
+    O, LSE = orc.closed_form(Q, K, V, None, causal, q_offset=128 if causal else 0)
+    Oa, La = orc.closed_form(Q, K[:, :, :128], V[:, :, :128], None, causal, q_offset=128 if causal else 0, k_offset=0)
+    Ob, Lb = orc.closed_form(Q, K[:, :, 128:], V[:, :, 128:], None, causal, q_offset=128 if causal else 0, k_offset=128)
+    Om, Lm = orc.merge_partials(Oa.float(), La.float(), Ob.float(), Lb.float())
+    assert (Om - O.float()).abs().max() < 1e-5 and (Lm - LSE.float()).abs().max() < 1e-5
+    # identity element
+    ninf = torch.full_like(La.float(), float("-inf"))
+    Oi, Li = orc.merge_partials(torch.zeros_like(Oa).float(), ninf, Oa.float(), La.float())
+    assert torch.equal(Li, La.float()) and (Oi - Oa.float()).abs().max() < 1e-6
