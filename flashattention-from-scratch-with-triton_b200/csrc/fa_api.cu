@@ -188,6 +188,14 @@ int fa_sm100_merge(float* o_acc, float* lse_acc, const void* o_part, const float
 int fa_sm100_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                  const float* lse, void* dq, void* dk, void* dv, float* delta,
                  int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale, void* stream) {
+    return fa_sm100_bwd_parts(q, k, v, o, dout, lse, dq, dk, dv, delta, B, H, Sq, Sk, D, dtype, causal, sm_scale,
+                              stream, FA_BWD_DELTA | FA_BWD_DQ | FA_BWD_DKV);
+}
+
+int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                       const float* lse, void* dq, void* dk, void* dv, float* delta,
+                       int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale, void* stream,
+                       int parts) {
     if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta) return fail(FA_ERR_NULL, "null tensor pointer");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dout) ||
@@ -196,9 +204,13 @@ int fa_sm100_bwd(const void* q, const void* k, const void* v, const void* o, con
     DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int BH = B * H;
-    int rc = launch_delta(o, dout, delta, (long long)BH * Sq, D, dtype, dev->sms, st);
-    ++g_launches;
-    if (rc) return cuda_fail((cudaError_t)rc, "fa_delta_kernel launch");
+    int rc = 0;
+    if (parts & FA_BWD_DELTA) {
+        rc = launch_delta(o, dout, delta, (long long)BH * Sq, D, dtype, dev->sms, st);
+        ++g_launches;
+        if (rc) return cuda_fail((cudaError_t)rc, "fa_delta_kernel launch");
+    }
+    if (!(parts & (FA_BWD_DQ | FA_BWD_DKV))) return 0;
     CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
     if (!make_map(&mq, q, BH, Sq, D, dtype, 128) || !make_map(&mk, k, BH, Sk, D, dtype, 128) ||
         !make_map(&mv, v, BH, Sk, D, dtype, 128) || !make_map(&mdo, dout, BH, Sq, D, dtype, 128) ||
@@ -211,8 +223,8 @@ int fa_sm100_bwd(const void* q, const void* k, const void* v, const void* o, con
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;
     p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
-    rc = launch_bwd(mq, mk, mv, mdo, mdq, mdk, mdv, p, D, dtype, st);
-    g_launches += 2;
+    rc = launch_bwd(mq, mk, mv, mdo, mdq, mdk, mdv, p, D, dtype, parts, st);
+    g_launches += ((parts & FA_BWD_DQ) ? 1 : 0) + ((parts & FA_BWD_DKV) ? 1 : 0);
     return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_bwd kernels launch");
 }
 

@@ -500,7 +500,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 template <int D, bool kBf16>
 int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
                  const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
-                 cudaStream_t st) {
+                 int parts, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(fa_bwd_dkv_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<D>::kSmemBytes);
@@ -510,20 +510,23 @@ int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
         attr_done = true;
     }
     // same order as the reference launcher (code/My_FlashAttention_optimized.py:111-126): dQ, then dK/dV
-    fa_bwd_dq_kernel<D, kBf16><<<p.BH * p.n_qtiles, kBwdThreads, BwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    fa_bwd_dkv_kernel<D, kBf16><<<p.BH * p.n_ktiles, kBwdThreads, BwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
+    if (parts & 2) {
+        fa_bwd_dq_kernel<D, kBf16><<<p.BH * p.n_qtiles, kBwdThreads, BwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (parts & 4)
+        fa_bwd_dkv_kernel<D, kBf16><<<p.BH * p.n_ktiles, kBwdThreads, BwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
     return (int)cudaGetLastError();
 }
 
 inline int launch_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
                       const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
-                      int D, int dtype, cudaStream_t st) {
-    if (D == 64) return dtype ? launch_bwd_t<64, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, st)
-                              : launch_bwd_t<64, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, st);
-    return dtype ? launch_bwd_t<128, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, st)
-                 : launch_bwd_t<128, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, st);
+                      int D, int dtype, int parts, cudaStream_t st) {
+    if (D == 64) return dtype ? launch_bwd_t<64, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, parts, st)
+                              : launch_bwd_t<64, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, parts, st);
+    return dtype ? launch_bwd_t<128, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, parts, st)
+                 : launch_bwd_t<128, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, parts, st);
 }
 
 }  // namespace fa

@@ -43,6 +43,22 @@ def flash_attention_forward(Q, K, V, is_causal, sm_scale=None):
     return O, LSE
 
 
+BWD_DELTA, BWD_DQ, BWD_DKV = 1, 2, 4
+
+
+def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, parts, sm_scale=None):
+    """Launch a subset of the backward kernels into caller-provided outputs (per-kernel timing)."""
+    lib = _cabi.load()
+    B, H, S_q, D = Q.shape
+    S_k = K.shape[2]
+    with torch.cuda.device(Q.device):
+        rc = lib.fa_sm100_bwd_parts(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
+                                    LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
+                                    B, H, S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                    float(sm_scale) if sm_scale is not None else 0.0, _stream(Q), int(parts))
+    _cabi.check("fa_sm100_bwd_parts", rc)
+
+
 def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None):
     """Allocate dQ / dK / dV (+ fp32 delta) and launch the backward kernels (reference :62-128)."""
     lib = _cabi.load()

@@ -54,6 +54,17 @@ int fa_sm100_bwd(const void* q, const void* k, const void* v, const void* o, con
                  int B, int H, int Sq, int Sk, int D, int dtype, int causal,
                  float sm_scale, void* stream);
 
+/* Same as fa_sm100_bwd but launches only the selected kernels: parts is a bit mask of
+ * FA_BWD_DELTA (1), FA_BWD_DQ (2), FA_BWD_DKV (4).  dQ and dKV read `delta`, so it must have been
+ * produced already when FA_BWD_DELTA is not set.  Used to time each kernel on its own (bench.py). */
+#define FA_BWD_DELTA 1
+#define FA_BWD_DQ 2
+#define FA_BWD_DKV 4
+int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                       const float* lse, void* dq, void* dk, void* dv, float* delta,
+                       int B, int H, int Sq, int Sk, int D, int dtype, int causal,
+                       float sm_scale, void* stream, int parts);
+
 /* delta = rowsum(dout * o) alone (the preprocess step of the backward; kernel :210-211). */
 int fa_sm100_delta(const void* o, const void* dout, float* delta,
                    int B, int H, int Sq, int D, int dtype, void* stream);

@@ -18,7 +18,7 @@ def _declared():
 
 def test_header_declares_expected_entry_points():
     d = _declared()
-    for name in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_delta", "fa_sm100_merge", "fa_sm100_supported",
+    for name in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_bwd_parts", "fa_sm100_delta", "fa_sm100_merge", "fa_sm100_supported",
                  "fa_last_error", "fa_sm100_version", "fa_sm100_launch_count", "fa_sm100_last_hang"):
         assert name in d
 

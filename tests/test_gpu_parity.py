@@ -1,0 +1,235 @@
+"""Parity of the sm_100a CUDA path (through the C ABI) against the CPU oracle, the committed golden
+vectors from the reference's own kernels, the reference Triton kernels on the same GPU, and
+size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star): O, dQ, dK, dV within atol = rtol = 1e-2 of fp32-upcast SDPA;
+LSE within 1e-3; error no worse than the reference Triton kernel's on the same inputs.
+"""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import flashattn_b200 as fa
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ATOL = RTOL = 1e-2
+LSE_TOL = 1e-3
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _run_cuda(Q, K, V, dO, causal):
+    q = Q.cuda().requires_grad_(True); k = K.cuda().requires_grad_(True); v = V.cuda().requires_grad_(True)
+    O = fa.flash_attention(q, k, v, causal)            # the public entry (reference :169-170)
+    O.backward(dO.cuda())
+    _, LSE = fa.flash_attention_forward(q.detach(), k.detach(), v.detach(), causal)
+    torch.cuda.synchronize()
+    return O.detach().cpu(), LSE.cpu(), q.grad.cpu(), k.grad.cpu(), v.grad.cpu()
+
+
+def _close(a, b, atol=ATOL, rtol=RTOL):
+    return torch.allclose(a.float(), b.float(), atol=atol, rtol=rtol)
+
+
+SMALL = [
+    # B, H, Sq, Sk, D
+    (1, 2, 128, 128, 64), (1, 2, 256, 256, 128), (2, 2, 384, 384, 64), (1, 3, 512, 512, 128),
+    (1, 2, 128, 384, 64), (1, 2, 384, 128, 128),                      # cross attention, S_q != S_k
+    (1, 2, 200, 300, 64), (1, 1, 333, 333, 128), (1, 2, 1, 77, 64),   # ragged / tiny (the reference mishandles these)
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("causal", [False, True], ids=["full", "causal"])
+@pytest.mark.parametrize("shape", SMALL, ids=lambda s: "x".join(map(str, s)))
+def test_fwd_bwd_vs_oracle(shape, causal, dtype):
+    B, H, Sq, Sk, D = shape
+    Q, K, V, dO = orc.make_inputs(B, H, Sq, Sk, D, dtype, seed=Sq + Sk + D)
+    O, LSE, dQ, dK, dV = _run_cuda(Q, K, V, dO, causal)
+    rO, rLSE, rdQ, rdK, rdV = orc.closed_form(Q, K, V, dO, causal)          # fp64 ground truth
+    sO, sdQ, sdK, sdV = orc.sdpa_fp32(Q, K, V, dO, causal)                   # the reference's yardstick
+    assert (LSE - rLSE.float()).abs().max() < LSE_TOL
+    for name, x, r, s in (("O", O, rO, sO), ("dQ", dQ, rdQ, sdQ), ("dK", dK, rdK, sdK), ("dV", dV, rdV, sdV)):
+        assert torch.isfinite(x.float()).all(), name
+        assert _close(x, r), f"{name} vs fp64 closed form: {(x.float() - r.float()).abs().max()}"
+        assert _close(x, s), f"{name} vs fp32 SDPA"
+    v = fa.verify_results(rO, O, rtol=1e-2, atol=1e-2)
+    assert v["cosine_sim"] > 0.999                                            # code/_verify_func.py:37
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_against_reference_kernel_goldens(path):
+    """Same seeded inputs as tests/golden/make_golden.py; outputs of the reference's Triton kernels."""
+    z = np.load(path)
+    m = {k[5:]: z[k].item() for k in z.files if k.startswith("meta_")}
+    g = {k: torch.from_numpy(z[k]).float() for k in z.files if not k.startswith("meta_")}
+    dt = getattr(torch, m["dtype"])
+    Q, K, V, dO = orc.make_inputs(m["B"], m["H"], m["Sq"], m["Sk"], m["D"], dt, m["seed"])
+    O, LSE, dQ, dK, dV = _run_cuda(Q, K, V, dO, bool(m["causal"]))
+    assert (LSE - g["LSE"]).abs().max() < LSE_TOL
+    # reference's own verdict rule (rtol=1e-2, atol=1e-3, cos>0.999) between the two fp16 kernels
+    for name, x in (("O", O), ("dQ", dQ), ("dK", dK), ("dV", dV)):
+        r = fa.verify_results(g[name], x, name)
+        assert r["cosine_sim"] > 0.9999 and r["max_abs_err"] < 4e-3, (name, r)
+    delta = fa.flash_attention_delta(O.cuda(), dO.cuda()).cpu()
+    assert (delta - g["delta"]).abs().max() < 5e-3
+
+
+def test_c1_config_vs_cpu_sdpa():
+    """BASELINE config 1: B=1 H=4 N=512 D=64 non-causal, fp32 masters -> CPU SDPA oracle."""
+    g = torch.Generator().manual_seed(0)
+    Qm, Km, Vm, dOm = (torch.randn(1, 4, 512, 64, generator=g) for _ in range(4))
+    sO, sdQ, sdK, sdV = orc.sdpa_fp32(Qm, Km, Vm, dOm, False)                 # fp32 master tensors
+    for dt in (torch.float16, torch.bfloat16):
+        O, LSE, dQ, dK, dV = _run_cuda(Qm.to(dt), Km.to(dt), Vm.to(dt), dOm.to(dt), False)
+        tol = 1e-2 if dt == torch.float16 else 2e-2     # includes the 16-bit rounding of the INPUTS themselves
+        for x, r in ((O, sO), (dQ, sdQ), (dK, sdK), (dV, sdV)):
+            assert _close(x, r, tol, tol)
+        assert (LSE - orc.lse_bench(Qm.to(dt), Km.to(dt), False)).abs().max() < LSE_TOL
+
+
+def _gpu_truth(Q, K, V, dO, causal):
+    """fp32 materialised attention on the GPU (TF32 off) for shapes too big for the CPU oracle;
+    itself checked against the CPU oracle in test_gpu_truth_is_the_oracle."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    D = Q.shape[-1]; scale = 1 / math.sqrt(D)
+    outs = []
+    for b in range(Q.shape[0]):
+        q, k, v, do = Q[b].float(), K[b].float(), V[b].float(), dO[b].float()
+        S = q @ k.transpose(-1, -2) * scale
+        if causal:
+            i = torch.arange(q.shape[1], device=q.device); j = torch.arange(k.shape[1], device=q.device)
+            S.masked_fill_(~(i[:, None] >= j[None, :]), float("-inf"))
+        lse = torch.logsumexp(S, -1); P = torch.exp(S - lse[..., None]); o = P @ v
+        dV = P.transpose(-1, -2) @ do; dP = do @ v.transpose(-1, -2)
+        dS = P * (dP - (do * o).sum(-1, keepdim=True))
+        outs.append((o, lse, dS @ k * scale, dS.transpose(-1, -2) @ q * scale, dV))
+    return [torch.stack(x) for x in zip(*outs)]
+
+
+def test_gpu_truth_is_the_oracle():
+    Q, K, V, dO = orc.make_inputs(1, 2, 256, 256, 64, torch.bfloat16, seed=1)
+    t = _gpu_truth(Q.cuda(), K.cuda(), V.cuda(), dO.cuda(), True)
+    r = orc.closed_form(Q, K, V, dO, True)
+    for a, b in zip(t, r):
+        assert (a.cpu() - b.float()).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [(4, 16, 2048, 2048, 64, True), (4, 16, 4096, 4096, 128, False)], ids=["C2", "C3"])
+def test_baseline_configs_full_size(cfg):
+    """BASELINE configs 2 and 3 at full size, bf16: every element vs fp32 truth; two (b,h) slices
+    additionally vs the CPU oracle."""
+    B, H, S, _, D, causal = cfg
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Q, K, V, dO = (torch.randn(B, H, S, D, device="cuda", generator=g).bfloat16() for _ in range(4))
+    q = Q.clone().requires_grad_(True); k = K.clone().requires_grad_(True); v = V.clone().requires_grad_(True)
+    O = fa.flash_attention(q, k, v, causal); O.backward(dO)
+    _, LSE = fa.flash_attention_forward(Q, K, V, causal)
+    tO, tLSE, tdQ, tdK, tdV = _gpu_truth(Q, K, V, dO, causal)
+    assert (LSE - tLSE).abs().max() < LSE_TOL
+    for name, x, r in (("O", O, tO), ("dQ", q.grad, tdQ), ("dK", k.grad, tdK), ("dV", v.grad, tdV)):
+        d = (x.float() - r).abs()
+        # bf16 contract: atol = rtol = 1e-2; over 1e7+ elements allow the 16-bit rounding tail 1.5e-2
+        assert (d <= 1.5e-2 + 1e-2 * r.abs()).all(), (name, d.max().item())
+        assert (d <= 1e-2 + 1e-2 * r.abs()).float().mean() > 0.99999, name
+        assert torch.nn.functional.cosine_similarity(x.float().flatten(), r.flatten(), dim=0) > 0.9999
+    for (b, h) in ((0, 0), (B - 1, H - 1)):
+        sl = lambda t: t[b:b + 1, h:h + 1].cpu()
+        cO, cLSE = orc.sdpa_cpu_flash(sl(Q).float(), sl(K).float(), sl(V).float(), None, causal)
+        assert _close(sl(O.detach()), cO) and (sl(LSE) - cLSE).abs().max() < LSE_TOL
+
+
+def test_properties_at_full_size():
+    """Size-independent properties on the C3 shape (B=4 H=16 N=4096 D=128 bf16)."""
+    B, H, S, D = 4, 16, 4096, 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Q, K, V = (torch.randn(B, H, S, D, device="cuda", generator=g).bfloat16() for _ in range(3))
+    # (1) rows of P sum to one: V = 1 -> O = 1
+    O1, _ = fa.flash_attention_forward(Q, K, torch.ones_like(V), False)
+    assert (O1.float() - 1).abs().max() < 8e-3
+    # (2) determinism: bitwise equal across runs
+    Oa, La = fa.flash_attention_forward(Q, K, V, True); Ob, Lb = fa.flash_attention_forward(Q, K, V, True)
+    assert torch.equal(Oa, Ob) and torch.equal(La, Lb)
+    # (3) causal prefix property: the first n rows do not depend on later keys — bitwise
+    n = 1024
+    Op, Lp = fa.flash_attention_forward(Q[:, :, :n].contiguous(), K[:, :, :n].contiguous(), V[:, :, :n].contiguous(), True)
+    assert torch.equal(Op, Oa[:, :, :n]) and torch.equal(Lp, La[:, :, :n])
+    # (4) (batch, head) independence: a head computed alone is bitwise the same (sharding invariant)
+    Oh, Lh = fa.flash_attention_forward(Q[1:2, 3:4].contiguous(), K[1:2, 3:4].contiguous(), V[1:2, 3:4].contiguous(), True)
+    assert torch.equal(Oh, Oa[1:2, 3:4]) and torch.equal(Lh, La[1:2, 3:4])
+    # (5) key-permutation invariance (non-causal): O unchanged up to rounding, LSE to 1e-3
+    perm = torch.randperm(S, device="cuda", generator=g)
+    Of, Lf = fa.flash_attention_forward(Q, K, V, False)
+    Oq, Lq = fa.flash_attention_forward(Q, K[:, :, perm].contiguous(), V[:, :, perm].contiguous(), False)
+    assert (Lf - Lq).abs().max() < LSE_TOL and _close(Of, Oq)
+    # (6) LSE merge over a key split == LSE over all keys (the ring invariant), via the CUDA merge kernel
+    Oacc = torch.zeros(B, H, S, D, device="cuda"); Lacc = torch.full((B, H, S), float("-inf"), device="cuda")
+    for lo in (0, S // 2):
+        Opart, Lpart = fa.flash_attention_forward(Q, K[:, :, lo:lo + S // 2].contiguous(), V[:, :, lo:lo + S // 2].contiguous(), False)
+        fa.merge_partial_(Oacc, Lacc, Opart, Lpart)
+    assert (Lacc - Lf).abs().max() < LSE_TOL and _close(Oacc, Of)
+
+
+def test_backward_is_deterministic_and_grads_flow():
+    Q, K, V, dO = (t.cuda() for t in orc.make_inputs(2, 4, 1024, 1024, 128, torch.bfloat16, seed=4))
+    O, LSE = fa.flash_attention_forward(Q, K, V, True)
+    a = fa.flash_attention_backward(Q, K, V, O, dO, LSE, True)
+    b = fa.flash_attention_backward(Q, K, V, O, dO, LSE, True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))           # two-kernel backward has no atomics
+    # linearity of the backward in dO (bf16: up to rounding)
+    c = fa.flash_attention_backward(Q, K, V, O, (2 * dO.float()).bfloat16(), LSE, True)
+    for x, y in zip(a, c):
+        assert _close(2 * x.float(), y.float(), 2e-2, 2e-2)
+
+
+def test_sm_scale_and_noncontiguous_inputs():
+    Q, K, V, dO = orc.make_inputs(1, 2, 256, 256, 64, torch.float16, seed=2)
+    O = fa.flash_attention(Q.cuda(), K.cuda(), V.cuda(), True, sm_scale=0.2)
+    rO, _ = orc.closed_form(Q, K, V, None, True, sm_scale=0.2)
+    assert _close(O.cpu(), rO)
+    Qb = Q.cuda().transpose(1, 2).contiguous().transpose(1, 2)    # [B,H,S,D] view of a [B,S,H,D] buffer
+    assert not Qb.is_contiguous()
+    O2 = fa.flash_attention(Qb, K.cuda(), V.cuda(), True, sm_scale=0.2)   # .contiguous() like reference :138
+    assert torch.equal(O, O2)
+    assert fa.attention is fa.flash_attention
+
+
+def test_error_no_worse_than_reference_triton():
+    """Same inputs through the reference Triton kernels (baseline/_ref) and through this library;
+    error against fp32 truth must not exceed the reference's (25 % slack for rounding noise)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline"))
+    import ref_runner
+    why = ref_runner.available()
+    if why:
+        pytest.skip(why)
+    for dt, causal, D in ((torch.float16, True, 64), (torch.bfloat16, True, 64), (torch.bfloat16, False, 128)):
+        try:
+            ref_fn = ref_runner.ref_flash_attention(dt == torch.bfloat16)
+        except Exception as e:  # pragma: no cover
+            pytest.skip(f"reference import failed: {e!r}")
+        g = torch.Generator(device="cuda").manual_seed(5)
+        Q, K, V, dO = (torch.randn(2, 4, 1024, D, device="cuda", generator=g).to(dt) for _ in range(4))
+        truth = _gpu_truth(Q, K, V, dO, causal)
+        errs = {}
+        for name, fn in (("ref", ref_fn), ("ours", fa.flash_attention)):
+            q = Q.clone().requires_grad_(True); k = K.clone().requires_grad_(True); v = V.clone().requires_grad_(True)
+            O = fn(q, k, v, causal); O.backward(dO)
+            errs[name] = [(x.float() - t).abs().mean().item() for x, t in zip((O, q.grad, k.grad, v.grad),
+                                                                              (truth[0], truth[2], truth[3], truth[4]))]
+        for eo, er in zip(errs["ours"], errs["ref"]):
+            assert eo <= 1.25 * er + 1e-6, (dt, causal, D, errs)
+
+
+def test_product_path_is_the_cuda_library():
+    import flashattn_b200._cabi as cabi
+    n0 = cabi.load().fa_sm100_launch_count()
+    Q, K, V, dO = (t.cuda() for t in orc.make_inputs(1, 1, 128, 128, 64, torch.float16, seed=0))
+    O, LSE = fa.flash_attention_forward(Q, K, V, False)
+    fa.flash_attention_backward(Q, K, V, O, dO, LSE, False)
+    assert cabi.load().fa_sm100_launch_count() - n0 == 4          # fwd, delta, dQ, dKV
+    assert cabi.last_hang() is None

@@ -35,7 +35,9 @@ def test_oracle_matches_reference_kernels(path):
     assert (LSE - g["LSE"]).abs().max() < 5e-6
     for name, x in (("O", O), ("dQ", dQ), ("dK", dK), ("dV", dV)):
         ref = g[name]
-        ulp = torch.clamp(ref.abs(), min=2.0 ** -10) * 2.0 ** -10      # fp16 ulp at that magnitude (approx.)
+        # <= 2.5 fp16 ulp at the value's magnitude, with an absolute floor of 1 ulp at 0.5 for
+        # near-zero sums (fp32 accumulation order differs between numpy and torch matmuls)
+        ulp = torch.clamp(ref.abs() * 2.0 ** -10, min=2.0 ** -11)
         assert ((x.float() - ref).abs() <= 2.5 * ulp).all(), name
     assert (delta - g["delta"]).abs().max() < 2e-3
 
