@@ -18,7 +18,7 @@ SYMBOLS = {
     "fa_sm100_bwd": (_i, [_vp] * 10 + [_i] * 7 + [_f, _vp]),
     "fa_sm100_bwd_parts": (_i, [_vp] * 10 + [_i] * 7 + [_f, _vp, _i]),
     "fa_sm100_delta": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "fa_sm100_merge": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fa_sm100_merge": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fa_sm100_supported": (_i, [_i, _i, _i, _i]),
     "fa_last_error": (ctypes.c_char_p, []),
     "fa_sm100_version": (_i, []),

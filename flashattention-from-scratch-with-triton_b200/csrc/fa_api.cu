@@ -176,11 +176,13 @@ int fa_sm100_delta(const void* o, const void* dout, float* delta, int B, int H, 
 }
 
 int fa_sm100_merge(float* o_acc, float* lse_acc, const void* o_part, const float* lse_part,
-                   int B, int H, int Sq, int D, int dtype, void* stream) {
+                   int B, int H, int Sq, int D, int dtype, int Sq_acc, int q_off, void* stream) {
     if (!o_acc || !lse_acc || !o_part || !lse_part) return fail(FA_ERR_NULL, "null tensor pointer");
     if (int rc = check_common(B, H, Sq, 1, D, dtype)) return rc;
+    if (q_off < 0 || Sq_acc < q_off + Sq) return fail(FA_ERR_SHAPE, "rows [%d, %d) do not fit an accumulator of %d rows", q_off, q_off + Sq, Sq_acc);
+    if (!aligned16(o_acc) || !aligned16(o_part)) return fail(FA_ERR_ALIGN, "o_acc/o_part must be 16-byte aligned");
     DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
-    int rc = launch_merge(o_acc, lse_acc, o_part, lse_part, (long long)B * H * Sq, D, dtype, dev->sms, (cudaStream_t)stream);
+    int rc = launch_merge(o_acc, lse_acc, o_part, lse_part, (long long)B * H * Sq, Sq, Sq_acc, q_off, D, dtype, dev->sms, (cudaStream_t)stream);
     ++g_launches;
     return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_merge_kernel launch");
 }

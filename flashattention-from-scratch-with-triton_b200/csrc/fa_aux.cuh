@@ -66,12 +66,13 @@ inline int launch_delta(const void* o, const void* dout, float* delta, long long
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(256) fa_merge_kernel(float4* __restrict__ o_acc, float* __restrict__ lse_acc,
                                                        const uint4* __restrict__ o_part, const float* __restrict__ lse_part,
-                                                       long long rows) {
+                                                       long long rows, int Sq, int Sq_acc, int q_off) {
     constexpr int TPR = D / 8;
     constexpr int RPB = 256 / TPR;
     const int sub = threadIdx.x % TPR;
     for (long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row < rows; row += (long long)gridDim.x * RPB) {
-        const float la = lse_acc[row], lb = lse_part[row];
+        const long long arow = (row / Sq) * Sq_acc + q_off + (row % Sq);     // row inside the accumulator
+        const float la = lse_acc[arow], lb = lse_part[row];
         const float mx = fmaxf(la, lb);
         float wa, wb, lnew;
         if (mx == -INFINITY) { wa = 0.f; wb = 0.f; lnew = -INFINITY; }
@@ -81,29 +82,29 @@ __global__ void __launch_bounds__(256) fa_merge_kernel(float4* __restrict__ o_ac
             lnew = mx + __logf(s);
             wa = ea / s; wb = eb / s;
         }
-        float4 a0 = o_acc[row * TPR * 2 + sub * 2], a1 = o_acc[row * TPR * 2 + sub * 2 + 1];
+        float4 a0 = o_acc[arow * TPR * 2 + sub * 2], a1 = o_acc[arow * TPR * 2 + sub * 2 + 1];
         float fb[8];
         unpack8<kBf16>(__ldg(o_part + row * TPR + sub), fb);
         a0.x = a0.x * wa + fb[0] * wb; a0.y = a0.y * wa + fb[1] * wb; a0.z = a0.z * wa + fb[2] * wb; a0.w = a0.w * wa + fb[3] * wb;
         a1.x = a1.x * wa + fb[4] * wb; a1.y = a1.y * wa + fb[5] * wb; a1.z = a1.z * wa + fb[6] * wb; a1.w = a1.w * wa + fb[7] * wb;
-        o_acc[row * TPR * 2 + sub * 2] = a0; o_acc[row * TPR * 2 + sub * 2 + 1] = a1;
+        o_acc[arow * TPR * 2 + sub * 2] = a0; o_acc[arow * TPR * 2 + sub * 2 + 1] = a1;
         // every thread of the row group has read lse_acc[row] before its leader overwrites it
         __syncwarp(row_group_mask<TPR>());
-        if (sub == 0) lse_acc[row] = lnew;
+        if (sub == 0) lse_acc[arow] = lnew;
     }
 }
 
 inline int launch_merge(float* o_acc, float* lse_acc, const void* o_part, const float* lse_part, long long rows,
-                        int D, int dtype, int sms, cudaStream_t st) {
+                        int Sq, int Sq_acc, int q_off, int D, int dtype, int sms, cudaStream_t st) {
     const int rpb = 256 / (D / 8);
     long long blocks = (rows + rpb - 1) / rpb;
     const long long cap = (long long)sms * 16;
     if (blocks > cap) blocks = cap;
     float4* oa = (float4*)o_acc; const uint4* op = (const uint4*)o_part;
-    if (D == 64) { if (dtype) fa_merge_kernel<64, true><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows);
-                   else fa_merge_kernel<64, false><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows); }
-    else         { if (dtype) fa_merge_kernel<128, true><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows);
-                   else fa_merge_kernel<128, false><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows); }
+    if (D == 64) { if (dtype) fa_merge_kernel<64, true><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off);
+                   else fa_merge_kernel<64, false><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off); }
+    else         { if (dtype) fa_merge_kernel<128, true><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off);
+                   else fa_merge_kernel<128, false><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off); }
     return (int)cudaGetLastError();
 }
 

@@ -121,14 +121,17 @@ def flash_attention_delta(O, dO):
     return delta
 
 
-def merge_partial_(O_acc, LSE_acc, O_part, LSE_part):
-    """In-place (O, LSE) merge of a partial attention over a disjoint key set (ring hops)."""
+def merge_partial_(O_acc, LSE_acc, O_part, LSE_part, q_off=0):
+    """In-place (O, LSE) merge of a partial attention over a disjoint key set (ring hops) into rows
+    [q_off, q_off + S_part) of the fp32 accumulators O_acc [B,H,S_acc,D], LSE_acc [B,H,S_acc]."""
     lib = _cabi.load()
     B, H, S_q, D = O_part.shape
+    S_acc = O_acc.shape[2]
     assert O_acc.dtype == torch.float32 and LSE_acc.dtype == torch.float32 and LSE_part.dtype == torch.float32
     assert O_acc.is_contiguous() and O_part.is_contiguous() and LSE_acc.is_contiguous() and LSE_part.is_contiguous()
+    assert O_acc.shape[:2] == O_part.shape[:2] and O_acc.shape[3] == D and LSE_acc.shape == O_acc.shape[:3]
     with torch.cuda.device(O_part.device):
         rc = lib.fa_sm100_merge(O_acc.data_ptr(), LSE_acc.data_ptr(), O_part.data_ptr(), LSE_part.data_ptr(),
-                                B, H, S_q, D, _DT[O_part.dtype], _stream(O_part))
+                                B, H, S_q, D, _DT[O_part.dtype], S_acc, int(q_off), _stream(O_part))
     _cabi.check("fa_sm100_merge", rc)
     return O_acc, LSE_acc

@@ -1,5 +1,14 @@
 mkdir -p gpurun_out
-timeout 120 python __graft_entry__.py smoke > gpurun_out/c4_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/c4_smoke.log
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/c4_pytest.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/c4_pytest.log
-timeout 600 python bench.py > gpurun_out/c4_bench.json 2> gpurun_out/c4_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/c4_bench.err; cat gpurun_out/c4_bench.json
-timeout 600 python bench.py --impl reference > gpurun_out/c4_bench_ref.json 2> gpurun_out/c4_bench_ref.err; echo "ref rc=$?"; tail -3 gpurun_out/c4_bench_ref.err; cat gpurun_out/c4_bench_ref.json
+CMD="python bench.py --steps 2 --warmup 3 --no-extras"
+$CMD > gpurun_out/c5_plain_c2.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/c5_launches_c2.csv $CMD > gpurun_out/c5_ncu1.log 2>&1
+echo "launch list rc=$?"
+$CMD > gpurun_out/c5_plain_c2b.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:fa_ -s 12 -c 4 -f -o gpurun_out/c5_prof_c2 $CMD > gpurun_out/c5_ncu2.log 2>&1
+echo "full c2 rc=$?"
+CMD3="python bench.py --steps 2 --warmup 3 --no-extras --workload C3"
+$CMD3 > gpurun_out/c5_plain_c3.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:fa_ -s 12 -c 4 -f -o gpurun_out/c5_prof_c3 $CMD3 > gpurun_out/c5_ncu3.log 2>&1
+echo "full c3 rc=$?"
+ls -la gpurun_out/ | tail -12
+tail -3 gpurun_out/c5_ncu2.log

@@ -70,12 +70,13 @@ int fa_sm100_delta(const void* o, const void* dout, float* delta,
                    int B, int H, int Sq, int D, int dtype, void* stream);
 
 /* Ring / partial attention support (no reference counterpart):
- * in-place merge of a partial result (o_part, lse_part) over a disjoint key set into the running
- * (o_acc fp32 [B,H,Sq,D], lse_acc fp32 [B,H,Sq]):
+ * in-place merge of a partial result (o_part [B,H,Sq,D] dtype, lse_part [B,H,Sq] fp32) computed over a
+ * disjoint key set into rows [q_off, q_off+Sq) of the running fp32 accumulators
+ * (o_acc [B,H,Sq_acc,D], lse_acc [B,H,Sq_acc]):
  *   lse = logaddexp(lse_acc, lse_part);  o_acc = o_acc*e^(lse_acc-lse) + o_part*e^(lse_part-lse).
  * lse = -inf partials are the identity. */
 int fa_sm100_merge(float* o_acc, float* lse_acc, const void* o_part, const float* lse_part,
-                   int B, int H, int Sq, int D, int dtype, void* stream);
+                   int B, int H, int Sq, int D, int dtype, int Sq_acc, int q_off, void* stream);
 
 /* Capability query, no launch: 1 if fa_sm100_fwd/bwd accept (D, dtype, Sq, Sk), else 0. */
 int fa_sm100_supported(int D, int dtype, int Sq, int Sk);

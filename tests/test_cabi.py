@@ -54,7 +54,8 @@ def test_argument_validation_without_gpu(lib):
     assert bwd(dt=-1) == -2
     assert bwd(dq=p + 8) == -5
     assert lib.fa_sm100_delta(p, None, p, 1, 1, 128, 64, 1, None) == -1
-    assert lib.fa_sm100_merge(p, p, p, None, 1, 1, 128, 64, 1, None) == -1
+    assert lib.fa_sm100_merge(p, p, p, None, 1, 1, 128, 64, 1, 128, 0, None) == -1
+    assert lib.fa_sm100_merge(p, p, p, p, 1, 1, 128, 64, 1, 128, 64, None) == -4
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
