@@ -194,6 +194,9 @@ def main():
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
+    # libraries (NCCL's version banner, Triton autotune chatter) may print to fd 1: keep stdout for the ONE JSON line
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,12 +226,13 @@ def main():
             # no usable copy of the reference kernels: time its CPU ground-truth path instead
             if rank == 0:
                 cb = cpu_baseline(B, H, S, D, causal)
-                print(json.dumps({"impl": "reference", "metric": "fwd_bwd_tflops", "value": cb["value"], "unit": "TFLOPS",
+                real_stdout.write(json.dumps({"impl": "reference", "metric": "fwd_bwd_tflops", "value": cb["value"], "unit": "TFLOPS",
                                   "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None,
                                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                                   "data": "synthetic", "config": {"workload": a.workload, "note": f"reference Triton kernels unavailable ({why}); CPU ground-truth path timed"},
                                   "cpu_baseline": cb,
-                                  "e2e": {"value": cb["value"], "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                                  "e2e": {"value": cb["value"], "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}) + "\n")
+                real_stdout.flush()
             return 0
         attn = ref_runner.ref_flash_attention(dtype_name == "bf16")
         ref_note = ("unmodified reference (baseline/_ref) through its public flash_attention(); fp16 because the shipped "
@@ -274,18 +278,31 @@ def main():
     if not a.no_extras:
         hin = [x.detach().cpu().pin_memory() for x in (Q, K, V, dO)]
         hout = [torch.empty_like(h).pin_memory() for h in hin]
-        dQ_, dK_, dV_, ddO = (torch.empty_like(x.detach()) for x in (Q, K, V, dO))
+        if a.impl == "ours":
+            # the product's host-buffer entry point: (b,h)-chunked H2D || kernels || D2H on three streams
+            from flashattn_b200.host_pipeline import HostAttentionPipeline
+            pipe = HostAttentionPipeline(B, H, S, S, D, dtype, causal, dev, chunks=int(os.environ.get('FA_E2E_CHUNKS', '4')),
+                                         buffers=int(os.environ.get('FA_E2E_BUFFERS', '2')))
+            e2e_note = ("flashattn_b200.host_pipeline.HostAttentionPipeline: Q,K,V,dO from pinned host memory, O,dQ,dK,dV back to "
+                        "pinned host memory every step; (b,h) chunks, H2D / kernels / D2H overlapped on 3 streams")
 
-        def e2e_step():
-            for dst, src in zip((dQ_, dK_, dV_, ddO), hin):
-                dst.copy_(src, non_blocking=True)
-            q = dQ_.requires_grad_(True); k = dK_.requires_grad_(True); v = dV_.requires_grad_(True)
-            O = attn(q, k, v, causal)
-            O.backward(ddO)
-            for dst, src in zip(hout, (O.detach(), q.grad, k.grad, v.grad)):
-                dst.copy_(src, non_blocking=True)
-            q.grad = None; k.grad = None; v.grad = None
-            dQ_.requires_grad_(False); dK_.requires_grad_(False); dV_.requires_grad_(False)
+            def e2e_step():
+                pipe.run(*hin, *hout)
+        else:
+            dQ_, dK_, dV_, ddO = (torch.empty_like(x.detach()) for x in (Q, K, V, dO))
+            e2e_note = ("stock reference API: serial H2D of Q,K,V,dO from pinned host memory, flash_attention + backward, "
+                        "serial D2H of O,dQ,dK,dV to pinned host memory, every step")
+
+            def e2e_step():
+                for dst, src in zip((dQ_, dK_, dV_, ddO), hin):
+                    dst.copy_(src, non_blocking=True)
+                q = dQ_.requires_grad_(True); k = dK_.requires_grad_(True); v = dV_.requires_grad_(True)
+                O = attn(q, k, v, causal)
+                O.backward(ddO)
+                for dst, src in zip(hout, (O.detach(), q.grad, k.grad, v.grad)):
+                    dst.copy_(src, non_blocking=True)
+                q.grad = None; k.grad = None; v.grad = None
+                dQ_.requires_grad_(False); dK_.requires_grad_(False); dV_.requires_grad_(False)
         barrier()
         te = time_steps(e2e_step, max(3, a.steps // 3), 3, flush)
         barrier()
@@ -295,7 +312,7 @@ def main():
         nbytes = sum(h.numel() * h.element_size() for h in hin)
         e2e = dict(value=world * flops_step / (e_ms * 1e-3) / 1e12, unit="TFLOPS", ms_per_step=e_ms,
                    h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes,
-                   note="Q,K,V,dO from pinned host memory; O,dQ,dK,dV back to pinned host memory, every step")
+                   note=e2e_note)
 
     line = {
         "metric": "fwd_bwd_tflops", "value": value, "unit": "TFLOPS", "n_gpus": world, "steps": a.steps,
@@ -342,7 +359,7 @@ def main():
         cb = cpu_baseline(B, H, S, D, causal)
         line["cpu_baseline"] = cb
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
     if dist_on:
         dist.barrier(); dist.destroy_process_group()
     return 0

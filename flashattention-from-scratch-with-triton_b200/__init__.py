@@ -6,9 +6,10 @@ Python identifier).  Hot path: hand-written sm_100a CUDA in ``csrc/`` behind the
 """
 from .interface import (FlashAttentionFunction, attention, flash_attention, flash_attention_backward, flash_attention_backward_parts,
                         flash_attention_delta, flash_attention_forward, merge_partial_)
+from .host_pipeline import HostAttentionPipeline, flash_attention_host
 from .verify import verify_results
 from .flops import attention_flops, tflops
 
 __all__ = ["flash_attention", "attention", "FlashAttentionFunction", "flash_attention_forward",
            "flash_attention_backward", "flash_attention_backward_parts", "flash_attention_delta", "merge_partial_", "verify_results",
-           "attention_flops", "tflops"]
+           "attention_flops", "tflops", "HostAttentionPipeline", "flash_attention_host"]

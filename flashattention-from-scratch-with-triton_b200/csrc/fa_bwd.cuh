@@ -14,9 +14,10 @@
 //   P^T = exp2(S^T c - LSE_i log2e) -> 16-bit over S^T; dV += P^T dO_i    (A from TMEM, B = dO_i MN-major)
 //   dS^T = P^T o (dP^T - delta_i)   -> 16-bit over dP^T; dK += dS^T Q_i   TMEM: dV [256,256+D) dK [256+D,..)
 // dQ kernel (one CTA per 128-row Q tile, loops over K/V tiles j):
-//   S = Q K_j^T, dP = dO V_j^T; dS = P o (dP - delta) -> 16-bit over dP; dQ += dS K_j (B = K_j MN-major)
-//   TMEM: S [0,128) dP [128,256) dQ [256,256+D).  S is released as soon as it is in registers, so
-//   S(j+1) runs under the exp/dS math of tile j.
+//   S = Q K_j^T, dP = dO V_j^T; dS = P o (dP - delta) -> 16-bit into its OWN double-buffered TMEM region;
+//   dQ += dS K_j (B = K_j MN-major).  TMEM: S [0,128) dP [128,256) dQ [256,256+D) dS0 dS1 (64 cols each)
+//   = exactly 512 columns at D=128.  S and dP are released as soon as they are in registers, so S(j+1) and
+//   dP(j+1) run under the exp/dS math of tile j and the math warps never wait for the tensor pipe.
 // Each warpgroup packs its 64 columns into the first 32 TMEM columns of ITS OWN half of the region
 // it overwrites, so the two warpgroups never touch each other's unread data; the MMA issuer
 // addresses the two 32-column runs explicitly per K=16 step.
@@ -46,9 +47,25 @@ template <int D> struct BwdCfg {
     static constexpr int kOffRes = 0;
     static constexpr int kOffStage = 2 * kTileBytes;
     static constexpr int kStageBytes = 2 * kTileBytes;
+    static constexpr int kStatStages = 8;                 // deep ring: statistics are tiny and latency-bound
     static constexpr int kOffStat = kOffStage + kStages * kStageBytes;
-    static constexpr int kOffBar = kOffStat + kStages * 1024;
-    static constexpr int kNumBars = 4 + 5 * kStages + 8;
+    static constexpr int kOffBar = kOffStat + kStatStages * 1024;
+    static constexpr int kNumBars = 8 + 3 * kStages + 2 * kStatStages + 4;
+    static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+};
+
+// dQ kernel: Q, dO resident; K_j lives from S(j) to dQ(j) (long), V_j only for dP(j) (short) -> separate rings,
+// K one slot deeper so that the loads keep a full tile of lead over the MMAs.
+template <int D> struct DqCfg {
+    static constexpr int kChunks = D / 64;
+    static constexpr int kTileBytes = 128 * D * 2;
+    static constexpr int kKStages = (D == 128) ? 3 : 4;
+    static constexpr int kVStages = (D == 128) ? 2 : 4;
+    static constexpr int kOffRes = 0;
+    static constexpr int kOffK = 2 * kTileBytes;
+    static constexpr int kOffV = kOffK + kKStages * kTileBytes;
+    static constexpr int kOffBar = kOffV + kVStages * kTileBytes;
+    static constexpr int kNumBars = 8 + 2 * kKStages + 2 * kVStages;
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 };
 
@@ -64,13 +81,14 @@ __device__ __forceinline__ void issue_scores(uint32_t d_tmem, uint32_t a_addr, u
 }
 // gradient MMA: D[tmem 128 x D] (+)= A[tmem: 128 lanes x 128 16-bit, two 32-column runs at a_tmem and
 // a_tmem+64] * B[smem 128 rows x D, MN-major]
-template <int D, bool kBf16>
+// (kSplitA) or one contiguous 64-column run (!kSplitA)
+template <int D, bool kBf16, bool kSplitA = true>
 __device__ __forceinline__ void issue_grad(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, bool acc) {
     constexpr uint32_t idesc = make_idesc(kBf16, false, true, 128, D);
     #pragma unroll
     for (int k = 0; k < 8; ++k)
-        umma_ts(d_tmem, a_tmem + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc(b_addr + k * 2048, 16384, 1024),
-                idesc, acc || k > 0);
+        umma_ts(d_tmem, a_tmem + (kSplitA ? (k >> 2) * 64 + (k & 3) * 8 : k * 8),
+                make_smem_desc(b_addr + k * 2048, 16384, 1024), idesc, acc || k > 0);
 }
 
 // TMEM accumulator half-row (D/2 columns starting at h*D/2) -> scaled 16-bit -> SWIZZLE_128B staging tile
@@ -93,7 +111,7 @@ __device__ __forceinline__ void stage_grad_half(uint32_t t_acc, uint8_t* stage, 
             #pragma unroll
             for (int i = 0; i < 4; ++i)
                 w[i] = pack2<kBf16>(__uint_as_float(v[g * 8 + 2 * i]) * mul, __uint_as_float(v[g * 8 + 2 * i + 1]) * mul);
-            *reinterpret_cast<uint4*>(chunk + sw128_offset(r, ((col0 & 63) >> 3) + g)) = make_uint4(w[0], w[1], w[2], w[3]);
+            sts128(smem_u32(chunk) + sw128_offset(r, ((col0 & 63) >> 3) + g), w[0], w[1], w[2], w[3]);
         }
     }
 }
@@ -118,11 +136,12 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     uint64_t* k_full = bars;            uint64_t* v_full = bars + 1;
     uint64_t* s_full = bars + 2;        uint64_t* dp_full = bars + 3;
     uint64_t* p_full = bars + 4;        uint64_t* ds_full = bars + 5;
-    uint64_t* acc_full = bars + 6;
+    uint64_t* acc_full = bars + 6;      uint64_t* s_full1 = bars + 7;    // second S^T buffer (kDoubleS)
     uint64_t* q_full = bars + 8;                        // [kStages]
     uint64_t* do_full = q_full + C::kStages;            // [kStages]
-    uint64_t* stat_full = do_full + C::kStages;         // [kStages]
-    uint64_t* stage_empty = stat_full + C::kStages;     // [kStages]
+    uint64_t* stage_empty = do_full + C::kStages;       // [kStages]
+    uint64_t* stat_full = stage_empty + C::kStages;     // [kStatStages]
+    uint64_t* stat_empty = stat_full + C::kStatStages;  // [kStatStages]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -132,12 +151,10 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     const int n_it = max(p.n_qtiles - i_start, 0);
 
     if (tid == 0) {
-        mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1);
+        mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(s_full1, 1); mbar_init(dp_full, 1);
         mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1);
-        for (int i = 0; i < C::kStages; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&do_full[i], 1); mbar_init(&stat_full[i], 1);
-            mbar_init(&stage_empty[i], 1);
-        }
+        for (int i = 0; i < C::kStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&do_full[i], 1); mbar_init(&stage_empty[i], 1); }
+        for (int i = 0; i < C::kStatStages; ++i) { mbar_init(&stat_full[i], 1); mbar_init(&stat_empty[i], 8); }
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -145,32 +162,49 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 256 + D;
+    // D=64 leaves 128 TMEM columns free: S^T is double-buffered there, so S^T(i+1) is ready before the math
+    // of tile i ends (the S -> P -> dV -> S chain otherwise dominates when the MMAs are short).
+    constexpr bool kDoubleS = (D == 64);
+    constexpr uint32_t kColST = 0, kColDPT = kDoubleS ? 256 : 128, kColDV = kDoubleS ? 384 : 256, kColDK = kColDV + D;
 
     if (warp == 11) {
         reg_dealloc<kBwdRegsOther>();
     } else if (warp == 10) {
         // ------------------------------ statistics loader ------------------------------
+        // Runs up to kStatStages tiles ahead of the math; the global loads of tile it+1 are in flight
+        // while tile it waits for its slot, so their latency never reaches the critical path.
         reg_dealloc<kBwdRegsOther>();
         const int lane = lane_id();
-        for (int it = 0; it < n_it; ++it) {
-            const int st = it % C::kStages;
-            mbar_wait(&stage_empty[st], ((it / C::kStages) & 1) ^ 1, 400);
+        const uint32_t stat_addr = smem_u32(sStat);
+        auto fetch = [&](int it, float (&nl)[4], float (&dl)[4]) {
             const int q0 = (i_start + it) * 128;
-            float* dst = sStat + st * 256;
             #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int c = lane + u * 32, row = q0 + c;
-                float nl = -INFINITY, dl = 0.f;          // out-of-range query rows: P = exp2(-inf) = 0
+                const int row = q0 + lane + u * 32;
+                nl[u] = -INFINITY; dl[u] = 0.f;           // out-of-range query rows: P = exp2(-inf) = 0
                 if (row < p.Sq) {
-                    const float l = p.lse[(size_t)bh * p.Sq + row];
-                    nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
-                    dl = p.delta[(size_t)bh * p.Sq + row];
+                    const float l = __ldg(p.lse + (size_t)bh * p.Sq + row);
+                    nl[u] = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+                    dl[u] = __ldg(p.delta + (size_t)bh * p.Sq + row);
                 }
-                dst[c] = nl; dst[128 + c] = dl;
+            }
+        };
+        float nl_n[4], dl_n[4];
+        if (n_it > 0) fetch(0, nl_n, dl_n);
+        for (int it = 0; it < n_it; ++it) {
+            float nl_c[4], dl_c[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) { nl_c[u] = nl_n[u]; dl_c[u] = dl_n[u]; }
+            if (it + 1 < n_it) fetch(it + 1, nl_n, dl_n);
+            const int ss = it % C::kStatStages;
+            mbar_wait(&stat_empty[ss], ((it / C::kStatStages) & 1) ^ 1, 400);
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                sts32(stat_addr + ss * 1024 + (lane + u * 32) * 4, nl_c[u]);
+                sts32(stat_addr + ss * 1024 + 512 + (lane + u * 32) * 4, dl_c[u]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&stat_full[st]);
+            if (lane == 0) mbar_arrive(&stat_full[ss]);
         }
     } else if (warp == 9) {
         // --------------------------------- TMA producer ---------------------------------
@@ -207,6 +241,10 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             mbar_wait(k_full, 0, 420);
             mbar_wait(&q_full[0], 0, 421); tc_fence_after();
             issue_scores<D, kBf16>(tmem + kColST, aK, aSt); tc_commit(s_full);
+            if (kDoubleS && n_it > 1) {
+                mbar_wait(&q_full[1 % C::kStages], 0, 428); tc_fence_after();
+                issue_scores<D, kBf16>(tmem + kColST + 128, aK, aSt + (1 % C::kStages) * C::kStageBytes); tc_commit(s_full1);
+            }
             mbar_wait(v_full, 0, 422);
             mbar_wait(&do_full[0], 0, 423); tc_fence_after();
             issue_scores<D, kBf16>(tmem + kColDPT, aV, aSt + C::kTileBytes); tc_commit(dp_full);
@@ -217,9 +255,17 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 const int st1 = (it + 1) % C::kStages;
                 const uint32_t ph1 = ((it + 1) / C::kStages) & 1;
                 const uint32_t aQ1 = aSt + st1 * C::kStageBytes;
+                const uint32_t sbuf = kDoubleS ? (it & 1) * 128 : 0;
                 mbar_wait(p_full, it & 1, 424); tc_fence_after();
-                issue_grad<D, kBf16>(tmem + kColDV, tmem + kColST, adO, it > 0);          // dV += P^T dO_i
-                if (more) {
+                issue_grad<D, kBf16>(tmem + kColDV, tmem + kColST + sbuf, adO, it > 0);   // dV += P^T dO_i
+                if (kDoubleS) {
+                    if (it + 2 < n_it) {                                                   // S^T(i+2) into the buffer dV(i) just read
+                        const int st2 = (it + 2) % C::kStages;
+                        mbar_wait(&q_full[st2], ((it + 2) / C::kStages) & 1, 425); tc_fence_after();
+                        issue_scores<D, kBf16>(tmem + kColST + sbuf, aK, aSt + st2 * C::kStageBytes);
+                        tc_commit((it & 1) ? s_full1 : s_full);
+                    }
+                } else if (more) {
                     mbar_wait(&q_full[st1], ph1, 425); tc_fence_after();
                     issue_scores<D, kBf16>(tmem + kColST, aK, aQ1); tc_commit(s_full);     // S^T(i+1)
                 }
@@ -244,20 +290,22 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const int kv_g = jt * 128 + r;
         const float c2 = p.scale_log2;
         for (int it = 0; it < n_it; ++it) {
-            const int st = it % C::kStages;
-            const float* stat = sStat + st * 256 + h * 64;
+            const int ss = it % C::kStatStages;
+            const uint32_t stat = smem_u32(sStat) + ss * 1024 + h * 256;
             const int q0 = (i_start + it) * 128 + h * 64;       // global query index of my column 0
-            mbar_wait(&stat_full[st], (it / C::kStages) & 1, 430);
-            mbar_wait(s_full, it & 1, 431);
+            mbar_wait(&stat_full[ss], (it / C::kStatStages) & 1, 430);
+            const uint32_t tSTi = tST + (kDoubleS ? (it & 1) * 128 : 0);
+            if (kDoubleS) mbar_wait((it & 1) ? s_full1 : s_full, (it >> 1) & 1, 431);
+            else mbar_wait(s_full, it & 1, 431);
             tc_fence_after();
             float pv[64];
             {
                 uint32_t s[2][32];
-                tmem_ld32(tST, s[0]); tmem_ld32(tST + 32, s[1]);
+                tmem_ld32(tSTi, s[0]); tmem_ld32(tSTi + 32, s[1]);
                 tc_wait_ld();
                 #pragma unroll
                 for (int c = 0; c < 64; c += 4) {
-                    const float4 nl = *reinterpret_cast<const float4*>(stat + c);
+                    const float4 nl = lds128(stat + c * 4);
                     pv[c]     = ex2_approx(fmaf(__uint_as_float(s[c >> 5][c & 31]),             c2, nl.x));
                     pv[c + 1] = ex2_approx(fmaf(__uint_as_float(s[(c + 1) >> 5][(c + 1) & 31]), c2, nl.y));
                     pv[c + 2] = ex2_approx(fmaf(__uint_as_float(s[(c + 2) >> 5][(c + 2) & 31]), c2, nl.z));
@@ -274,7 +322,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 uint32_t pk[16];
                 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] = pack2<kBf16>(pv[q * 32 + 2 * i], pv[q * 32 + 2 * i + 1]);
-                tmem_st16(tST + q * 16, pk);
+                tmem_st16(tSTi + q * 16, pk);
             }
             tc_wait_st(); tc_fence_before();
             mbar_arrive(p_full);
@@ -290,7 +338,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
                         const int c = q * 32 + 2 * i;
-                        const float4 dl = *reinterpret_cast<const float4*>(stat + 128 + c);
+                        const float4 dl = lds128(stat + 512 + c * 4);
                         const float d0 = pv[c] * (__uint_as_float(dp[q][2 * i]) - dl.x);
                         const float d1 = pv[c + 1] * (__uint_as_float(dp[q][2 * i + 1]) - dl.y);
                         const float d2 = pv[c + 2] * (__uint_as_float(dp[q][2 * i + 2]) - dl.z);
@@ -302,6 +350,8 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             }
             tc_wait_st(); tc_fence_before();
             mbar_arrive(ds_full);
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&stat_empty[ss]);    // this warp is done with the slot's statistics
         }
         // epilogue: dV, dK*scale -> 16-bit -> smem (over V, K) -> TMA store
         if (n_it > 0) { mbar_wait(acc_full, 0, 433); tc_fence_after(); }
@@ -332,20 +382,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                  const __grid_constant__ CUtensorMap mapdQ, const BwdParams p) {
-    using C = BwdCfg<D>;
+    using C = DqCfg<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem + C::kOffRes;
     uint8_t* sdO = sQ + C::kTileBytes;
-    uint8_t* sStage = smem + C::kOffStage;             // per stage: K_j then V_j
+    uint8_t* sKr = smem + C::kOffK;                    // K ring
+    uint8_t* sVr = smem + C::kOffV;                    // V ring
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
     uint64_t* q_full = bars;            uint64_t* do_full = bars + 1;
     uint64_t* s_full = bars + 2;        uint64_t* dp_full = bars + 3;
     uint64_t* s_empty = bars + 4;       uint64_t* ds_full = bars + 5;
-    uint64_t* acc_full = bars + 6;
-    uint64_t* k_full = bars + 8;                        // [kStages]
-    uint64_t* v_full = k_full + C::kStages;             // [kStages]
-    uint64_t* stage_empty = v_full + C::kStages;        // [kStages]
+    uint64_t* acc_full = bars + 6;      uint64_t* dp_empty = bars + 7;
+    uint64_t* k_full = bars + 8;                        // [kKStages]
+    uint64_t* k_empty = k_full + C::kKStages;           // [kKStages]
+    uint64_t* v_full = k_empty + C::kKStages;           // [kVStages]
+    uint64_t* v_empty = v_full + C::kVStages;           // [kVStages]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -355,8 +407,9 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
     if (tid == 0) {
         mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1);
-        mbar_init(s_empty, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1);
-        for (int i = 0; i < C::kStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&stage_empty[i], 1); }
+        mbar_init(s_empty, 256); mbar_init(dp_empty, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1);
+        for (int i = 0; i < C::kKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < C::kVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -364,7 +417,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256;
+    constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDS = 256 + D;   // dS buffers: kColDS + 64*(j&1)
 
     if (warp >= 10) {
         reg_dealloc<kBwdRegsOther>();
@@ -376,52 +429,49 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             #pragma unroll
             for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh);
             for (int it = 0; it < n_it; ++it) {
-                const int st = it % C::kStages;
-                uint8_t* sKj = sStage + st * C::kStageBytes;
-                uint8_t* sVj = sKj + C::kTileBytes;
-                mbar_wait(&stage_empty[st], ((it / C::kStages) & 1) ^ 1, 510);
-                mbar_arrive_expect_tx(&k_full[st], C::kTileBytes);
+                const int ks = it % C::kKStages, vs = it % C::kVStages;
+                uint8_t* sKj = sKr + ks * C::kTileBytes;
+                uint8_t* sVj = sVr + vs * C::kTileBytes;
+                mbar_wait(&k_empty[ks], ((it / C::kKStages) & 1) ^ 1, 510);
+                mbar_arrive_expect_tx(&k_full[ks], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sKj + c * 16384, &mapK, &k_full[st], c * 64, it * 128, bh);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, bh);
                 if (it == 0) {
                     mbar_arrive_expect_tx(do_full, C::kTileBytes);
                     #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sdO + c * 16384, &mapdO, do_full, c * 64, iq * 128, bh);
                 }
-                mbar_arrive_expect_tx(&v_full[st], C::kTileBytes);
+                mbar_wait(&v_empty[vs], ((it / C::kVStages) & 1) ^ 1, 511);
+                mbar_arrive_expect_tx(&v_full[vs], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sVj + c * 16384, &mapV, &v_full[st], c * 64, it * 128, bh);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, bh);
             }
         }
     } else if (warp == 8) {
         reg_dealloc<kBwdRegsOther>();
         if (lane_id() == 0) {
-            const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aSt = smem_u32(sStage);
+            const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKr = smem_u32(sKr), aVr = smem_u32(sVr);
             mbar_wait(q_full, 0, 520);
             mbar_wait(&k_full[0], 0, 521); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColS, aQ, aSt); tc_commit(s_full);
+            issue_scores<D, kBf16>(tmem + kColS, aQ, aKr); tc_commit(s_full);
             mbar_wait(do_full, 0, 522);
             mbar_wait(&v_full[0], 0, 523); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColDP, adO, aSt + C::kTileBytes); tc_commit(dp_full);
+            issue_scores<D, kBf16>(tmem + kColDP, adO, aVr); tc_commit(dp_full); tc_commit(&v_empty[0]);
             for (int it = 0; it < n_it; ++it) {
-                const int st = it % C::kStages;
-                const uint32_t aK = aSt + st * C::kStageBytes;
-                const bool more = it + 1 < n_it;
-                const int st1 = (it + 1) % C::kStages;
-                const uint32_t ph1 = ((it + 1) / C::kStages) & 1;
-                const uint32_t aK1 = aSt + st1 * C::kStageBytes;
-                if (more) {
+                const int ks = it % C::kKStages;
+                if (it + 1 < n_it) {
+                    const int ks1 = (it + 1) % C::kKStages, vs1 = (it + 1) % C::kVStages;
                     mbar_wait(s_empty, it & 1, 524);               // S(it) is in registers
-                    mbar_wait(&k_full[st1], ph1, 525); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColS, aQ, aK1); tc_commit(s_full);          // S(j+1)
+                    mbar_wait(&k_full[ks1], ((it + 1) / C::kKStages) & 1, 525); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColS, aQ, aKr + ks1 * C::kTileBytes); tc_commit(s_full);     // S(j+1)
+                    mbar_wait(dp_empty, it & 1, 528);              // dP(it) is in registers
+                    mbar_wait(&v_full[vs1], ((it + 1) / C::kVStages) & 1, 527); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColDP, adO, aVr + vs1 * C::kTileBytes); tc_commit(dp_full);  // dP(j+1)
+                    tc_commit(&v_empty[vs1]);
                 }
                 mbar_wait(ds_full, it & 1, 526); tc_fence_after();
-                issue_grad<D, kBf16>(tmem + kColDQ, tmem + kColDP, aK, it > 0);                // dQ += dS K_j
-                tc_commit(&stage_empty[st]);
-                if (more) {
-                    mbar_wait(&v_full[st1], ph1, 527); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColDP, adO, aK1 + C::kTileBytes); tc_commit(dp_full);   // dP(j+1)
-                }
+                issue_grad<D, kBf16, false>(tmem + kColDQ, tmem + kColDS + (it & 1) * 64, aKr + ks * C::kTileBytes, it > 0);   // dQ += dS K_j
+                tc_commit(&k_empty[ks]);
             }
             tc_commit(acc_full);
         }
@@ -432,6 +482,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem + lane_field + kColS + h * 64;
         const uint32_t tDP = tmem + lane_field + kColDP + h * 64;
+        const uint32_t tDS = tmem + lane_field + kColDS + h * 32;      // + 64 * (it & 1)
         const int row_g = iq * 128 + r;
         const float c2 = p.scale_log2;
         float nl = -INFINITY, dl = 0.f;
@@ -466,6 +517,9 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 uint32_t dp[2][32];
                 tmem_ld32(tDP, dp[0]); tmem_ld32(tDP + 32, dp[1]);
                 tc_wait_ld();
+                tc_fence_before();
+                mbar_arrive(dp_empty);
+                // dS(it) goes to buffer it&1; its previous reader dQ(it-2) completed before dp_full(it) fired
                 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     uint32_t pk[16];
@@ -475,7 +529,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         pk[i] = pack2<kBf16>(pv[c] * (__uint_as_float(dp[q][2 * i]) - dl),
                                              pv[c + 1] * (__uint_as_float(dp[q][2 * i + 1]) - dl));
                     }
-                    tmem_st16(tDP + q * 16, pk);
+                    tmem_st16(tDS + (it & 1) * 64 + q * 16, pk);
                 }
             }
             tc_wait_st(); tc_fence_before();
@@ -505,13 +559,13 @@ int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(fa_bwd_dkv_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(fa_bwd_dq_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<D>::kSmemBytes);
+        e = cudaFuncSetAttribute(fa_bwd_dq_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
     // same order as the reference launcher (code/My_FlashAttention_optimized.py:111-126): dQ, then dK/dV
     if (parts & 2) {
-        fa_bwd_dq_kernel<D, kBf16><<<p.BH * p.n_qtiles, kBwdThreads, BwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
+        fa_bwd_dq_kernel<D, kBf16><<<p.BH * p.n_qtiles, kBwdThreads, DqCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }

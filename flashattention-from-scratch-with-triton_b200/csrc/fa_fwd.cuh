@@ -11,6 +11,9 @@
 // the first 64 columns of S_t and is consumed as the A operand straight from TMEM.
 // The two tiles ping-pong: while warpgroup 0 runs softmax on S0(j+1), the tensor core runs
 // P1(j) V(j) and S1(j+1).
+// D=64 leaves 128 TMEM columns free: there P_t gets its own region (kSepP), so S_t(j+1) is issued as soon
+// as S_t(j) sits in the softmax registers instead of after P_t(j) V(j) — the softmax warpgroups then
+// never wait for the tensor pipe (the exp2 unit is the bound at D=64).
 #pragma once
 #include "fa_ptx.cuh"
 
@@ -36,7 +39,8 @@ template <int D> struct FwdCfg {
     static constexpr int kOffKV = 2 * kTileBytes;
     static constexpr int kOffO = kOffKV + kStages * kTileBytes;
     static constexpr int kOffBar = kOffO + 2 * kOStageBytes;
-    static constexpr int kNumBars = 2 + 2 + 2 * kStages + 2 + 2 + 2 + 2 + 2 + 2;
+    static constexpr bool kSepP = (D == 64);               // P in its own TMEM columns [384,512)
+    static constexpr int kNumBars = 2 + 2 + 2 * kStages + 2 + 2 + 2 + 2 + 2 + 2 + 2 + 2;
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 64 + 1024;   // +1024: manual alignment slack
 };
 
@@ -75,7 +79,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA (P_t in TMEM, O_t rescaled)
     uint64_t* o_full = p_full + 2;              // [2]  MMA -> softmax (last P V of the item done)
     uint64_t* o_empty = o_full + 2;             // [2]  softmax -> MMA (O_t drained from TMEM)
-    uint64_t* sched_full = o_empty + 2;         // [2]
+    uint64_t* s_empty = o_empty + 2;            // [2]  softmax -> MMA (S_t is in registers)           (kSepP)
+    uint64_t* pv_done = s_empty + 2;            // [2]  MMA -> softmax (P_t V of this iteration done)  (kSepP)
+    uint64_t* sched_full = pv_done + 2;         // [2]
     uint64_t* sched_empty = sched_full + 2;     // [2]
     volatile int* sched_item = reinterpret_cast<volatile int*>(sched_empty + 2);   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sched_item) + 2);
@@ -88,6 +94,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
             mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 128);
+            mbar_init(&s_empty[i], 128); mbar_init(&pv_done[i], 1);
             mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 9);   // MMA thread + 8 softmax warps
         }
         for (int i = 0; i < C::kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
@@ -154,6 +161,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             const uint32_t sq_addr = smem_u32(sQ), skv_addr = smem_u32(sKV);
             uint32_t kv_cnt = 0;
             uint32_t ph_q = 0, ph_p = 0, ph_oe = 0;      // bit t = parity to wait for next
+            uint32_t ph_sempty = 0;
             auto kv_wait = [&](uint32_t cnt) {
                 mbar_wait(&kv_full[cnt % C::kStages], (cnt / C::kStages) & 1, 200);
             };
@@ -170,7 +178,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const uint32_t b = skv_addr + st * C::kTileBytes;
                 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_ts(tmem + 256 + t * D, tmem + t * 128 + k * 8, make_smem_desc(b + k * 2048, 16384, 1024),
+                    umma_ts(tmem + 256 + t * D, tmem + (C::kSepP ? 384 + t * 64 : t * 128) + k * 8, make_smem_desc(b + k * 2048, 16384, 1024),
                             idesc_pv, acc || k > 0);
             };
             for (uint32_t it = 0;; ++it) {
@@ -199,38 +207,81 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     }
                     tc_commit(&kv_empty[st]); ++kv_cnt;
                 }
-                for (int j = 0; j < n; ++j) {
-                    const uint32_t vst = kv_cnt % C::kStages;
-                    const uint32_t kst = (kv_cnt + 1) % C::kStages;
-                    const bool more = (j + 1 < n);
-                    kv_wait(kv_cnt);                       // V(j)
-                    if (j < n0) {
-                        mbar_wait(&p_full[0], ph_p & 1, 204); ph_p ^= 1;
-                        if (j == 0) { mbar_wait(&o_empty[0], (ph_oe & 1) ^ 1, 205); ph_oe ^= 1; }
-                        tc_fence_after();
-                        issue_pv(0, vst, j > 0);
-                        if (j == n0 - 1) tc_commit(&o_full[0]);
-                    }
-                    if (more) kv_wait(kv_cnt + 1);         // K(j+1)
-                    if (j + 1 < n0) {
-                        tc_fence_after();
-                        issue_s(0, kst); tc_commit(&s_full[0]);
-                        if (j + 1 == n0 - 1) tc_commit(&q_empty[0]);
-                    }
-                    if (j < n1) {
-                        mbar_wait(&p_full[1], (ph_p >> 1) & 1, 206); ph_p ^= 2;
-                        if (j == 0) { mbar_wait(&o_empty[1], ((ph_oe >> 1) & 1) ^ 1, 207); ph_oe ^= 2; }
-                        tc_fence_after();
-                        issue_pv(1, vst, j > 0);
-                        if (j == n1 - 1) tc_commit(&o_full[1]);
-                    }
-                    tc_commit(&kv_empty[vst]); ++kv_cnt;
-                    if (more) {
-                        if (j + 1 < n1) {
-                            issue_s(1, kst); tc_commit(&s_full[1]);
-                            if (j + 1 == n1 - 1) tc_commit(&q_empty[1]);
+                if constexpr (C::kSepP) {
+                    // ring elements of this item: K(j) = base + 2j, V(j) = base + 2j + 1 (K(0) already consumed)
+                    const uint32_t base = kv_cnt - 1;
+                    uint32_t ph_se = ph_sempty;
+                    for (int j = 0; j < n; ++j) {
+                        const uint32_t vcnt = base + 2 * j + 1, kcnt = base + 2 * j + 2;
+                        const uint32_t vst = vcnt % C::kStages, kst = kcnt % C::kStages;
+                        if (j + 1 < n) {                       // S_t(j+1) as soon as S_t(j) is in registers
+                            kv_wait(kcnt);
+                            if (j + 1 < n0) {
+                                mbar_wait(&s_empty[0], ph_se & 1, 208); ph_se ^= 1; tc_fence_after();
+                                issue_s(0, kst); tc_commit(&s_full[0]);
+                                if (j + 1 == n0 - 1) tc_commit(&q_empty[0]);
+                            }
+                            if (j + 1 < n1) {
+                                mbar_wait(&s_empty[1], (ph_se >> 1) & 1, 209); ph_se ^= 2; tc_fence_after();
+                                issue_s(1, kst); tc_commit(&s_full[1]);
+                                if (j + 1 == n1 - 1) tc_commit(&q_empty[1]);
+                            }
+                            tc_commit(&kv_empty[kst]);
                         }
-                        tc_commit(&kv_empty[kst]); ++kv_cnt;
+                        kv_wait(vcnt);
+                        if (j < n0) {
+                            mbar_wait(&p_full[0], ph_p & 1, 204); ph_p ^= 1;
+                            if (j == 0) { mbar_wait(&o_empty[0], (ph_oe & 1) ^ 1, 205); ph_oe ^= 1; }
+                            tc_fence_after();
+                            issue_pv(0, vst, j > 0); tc_commit(&pv_done[0]);
+                        }
+                        if (j < n1) {
+                            mbar_wait(&p_full[1], (ph_p >> 1) & 1, 206); ph_p ^= 2;
+                            if (j == 0) { mbar_wait(&o_empty[1], ((ph_oe >> 1) & 1) ^ 1, 207); ph_oe ^= 2; }
+                            tc_fence_after();
+                            issue_pv(1, vst, j > 0); tc_commit(&pv_done[1]);
+                        }
+                        tc_commit(&kv_empty[vst]);
+                    }
+                    // the last S_t of the item is never followed by an s_empty wait: skip those phases
+                    if (n0 > 0) ph_se ^= 1;
+                    if (n1 > 0) ph_se ^= 2;
+                    ph_sempty = ph_se;
+                    kv_cnt = base + 2 * n;
+                } else {
+                for (int j = 0; j < n; ++j) {
+                        const uint32_t vst = kv_cnt % C::kStages;
+                        const uint32_t kst = (kv_cnt + 1) % C::kStages;
+                        const bool more = (j + 1 < n);
+                        kv_wait(kv_cnt);                       // V(j)
+                        if (j < n0) {
+                            mbar_wait(&p_full[0], ph_p & 1, 204); ph_p ^= 1;
+                            if (j == 0) { mbar_wait(&o_empty[0], (ph_oe & 1) ^ 1, 205); ph_oe ^= 1; }
+                            tc_fence_after();
+                            issue_pv(0, vst, j > 0);
+                            if (j == n0 - 1) tc_commit(&o_full[0]);
+                        }
+                        if (more) kv_wait(kv_cnt + 1);         // K(j+1)
+                        if (j + 1 < n0) {
+                            tc_fence_after();
+                            issue_s(0, kst); tc_commit(&s_full[0]);
+                            if (j + 1 == n0 - 1) tc_commit(&q_empty[0]);
+                        }
+                        if (j < n1) {
+                            mbar_wait(&p_full[1], (ph_p >> 1) & 1, 206); ph_p ^= 2;
+                            if (j == 0) { mbar_wait(&o_empty[1], ((ph_oe >> 1) & 1) ^ 1, 207); ph_oe ^= 2; }
+                            tc_fence_after();
+                            issue_pv(1, vst, j > 0);
+                            if (j == n1 - 1) tc_commit(&o_full[1]);
+                        }
+                        tc_commit(&kv_empty[vst]); ++kv_cnt;
+                        if (more) {
+                            if (j + 1 < n1) {
+                                issue_s(1, kst); tc_commit(&s_full[1]);
+                                if (j + 1 == n1 - 1) tc_commit(&q_empty[1]);
+                            }
+                            tc_commit(&kv_empty[kst]); ++kv_cnt;
+                        }
                     }
                 }
             }
@@ -243,8 +294,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem + lane_field + t * 128;
         const uint32_t tO = tmem + lane_field + 256 + t * D;
+        const uint32_t tP = C::kSepP ? tmem + lane_field + 384 + t * 64 : tS;    // 16-bit P (A operand of P V)
         uint8_t* sOt = sO + t * C::kOStageBytes;
-        uint32_t ph_s = 0, ph_o = 0;
+        uint32_t ph_s = 0, ph_o = 0, ph_pv = 0;
         const float c2 = p.scale_log2;
         for (uint32_t it = 0;; ++it) {
             const uint32_t slot = it & 1;
@@ -266,6 +318,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 #pragma unroll
                 for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, s[q]);
                 tc_wait_ld();
+                if constexpr (C::kSepP) { tc_fence_before(); mbar_arrive(&s_empty[t]); }   // S_t(j+1) may overwrite S_t now
                 // element mask only on tiles that straddle the diagonal or the end of K
                 int cmax = p.Sk - 1 - j * 128;                              // last valid column in this tile
                 if (p.causal) cmax = min(cmax, row_g - j * 128);
@@ -286,6 +339,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 if (j == 0) {
                     m = m_new;
                 } else {
+                    if constexpr (C::kSepP) {      // P_t(j-1) V(j-1) must be complete before O_t or P_t is touched
+                        mbar_wait(&pv_done[t], ph_pv, 303); ph_pv ^= 1; tc_fence_after();
+                    }
                     // lazy rescale (warp-uniform decision: tcgen05.ld/st are warp-collective)
                     const bool need = (m_new - m) * c2 > kLazyRescaleLog2;
                     if (__any_sync(0xffffffffu, need)) {
@@ -315,7 +371,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         l0 += p0; l1 += p1;                                  // fp32, before rounding (ref :111)
                         pk[i] = pack2<kBf16>(p0, p1);
                     }
-                    tmem_st16(tS + q * 16, pk);
+                    tmem_st16(tP + q * 16, pk);
                 }
                 l += l0 + l1;
                 tc_wait_st();
@@ -323,7 +379,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 mbar_arrive(&p_full[t]);
             }
             // ---------------- epilogue: O = o / l, LSE = m*scale + ln(l) ----------------
-            mbar_wait(&o_full[t], ph_o, 302); ph_o ^= 1;
+            if constexpr (C::kSepP) { mbar_wait(&pv_done[t], ph_pv, 302); ph_pv ^= 1; }
+            else { mbar_wait(&o_full[t], ph_o, 302); ph_o ^= 1; }
             tc_fence_after();
             const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
             #pragma unroll

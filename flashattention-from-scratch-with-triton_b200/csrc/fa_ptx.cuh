@@ -275,6 +275,20 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t c16) {
     return row * 128u + ((c16 ^ (row & 7u)) << 4);
 }
 
+// explicit shared-window accesses (pointers derived from the aligned dynamic-smem base are otherwise
+// compiled as generic LD/ST)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, float a) {
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(saddr), "f"(a) : "memory");
+}
+
 // register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it)
 template <int N> __device__ __forceinline__ void reg_alloc()   { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
