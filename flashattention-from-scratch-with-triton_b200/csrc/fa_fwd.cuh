@@ -2,10 +2,11 @@
 // Replaces flash_attention_forward_kernel (reference code/_flash_attention_kernel_optimized.py:34-129)
 // with a persistent, warp-specialized tcgen05 / TMA kernel.
 //
-// CTA = 384 threads (warps 10-11 idle; they donate registers via setmaxnreg), one CTA per SM, each work item = 256 query rows of one (batch, head):
+// CTA = 384 threads (warp 11 idle; the third warpgroup donates registers via setmaxnreg), one CTA per SM, each work item = 256 query rows of one (batch, head):
 //   warps 0-3  softmax warpgroup for Q tile 0 (rows 0..127 of the item; thread r <-> TMEM lane r)
 //   warps 4-7  softmax warpgroup for Q tile 1
 //   warp  8    MMA issuer (one thread): S_t = Q_t K^T, O_t += P_t V on tcgen05, accumulators in TMEM
+//              (at D=64, where P has its own TMEM region, warp 10 issues for tile 1 and warp 8 for tile 0)
 //   warp  9    TMA producer (one thread) + dynamic tile scheduler
 // TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D); P_t (16-bit) overwrites
 // the first 64 columns of S_t and is consumed as the A operand straight from TMEM.
@@ -95,9 +96,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
             mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 128);
             mbar_init(&s_empty[i], 128); mbar_init(&pv_done[i], 1);
-            mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 9);   // MMA thread + 8 softmax warps
+            mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], C::kSepP ? 10 : 9);  // MMA thread(s) + 8 softmax warps
         }
-        for (int i = 0; i < C::kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < C::kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], C::kSepP ? 2 : 1); }   // released by every MMA thread
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -106,8 +107,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 10) {
-        reg_dealloc<kFwdRegsOther>();     // idle warps (register donors)
+    if (warp == 11) {
+        reg_dealloc<kFwdRegsOther>();     // idle warp (register donor)
     } else if (warp == 9) {
         // ================================ TMA producer + scheduler ================================
         reg_dealloc<kFwdRegsOther>();
@@ -152,16 +153,103 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 item = (int)atomicAdd(p.sched, 1u) + (int)gridDim.x;
             }
         }
-    } else if (warp == 8) {
-        // ======================================= MMA issuer =======================================
+    } else if (warp == 8 || warp == 10) {
+        // ===================================== MMA issuers =====================================
+        // One issuing thread PER Q tile (warp 8 -> tile 0, warp 10 -> tile 1).  The two tiles' MMA chains
+        // are independent (own TMEM regions, read-only K/V), so neither tile ever waits behind a barrier
+        // that belongs to the other.  Each K/V ring slot is released by both threads (kv_empty count 2).
         reg_dealloc<kFwdRegsOther>();
+        if constexpr (C::kSepP) {
+        if (lane_id() == 0) {
+            const int t = (warp == 8) ? 0 : 1;
+            constexpr uint32_t idesc_s = make_idesc(kBf16, false, false, 128, 128);
+            constexpr uint32_t idesc_pv = make_idesc(kBf16, false, true, 128, D);
+            const uint32_t sq_addr = smem_u32(sQ) + t * C::kTileBytes, skv_addr = smem_u32(sKV);
+            const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * D;
+            const uint32_t tP = C::kSepP ? tmem + 384 + t * 64 : tS;
+            uint32_t kv_cnt = 0;                           // ring element index of K(0) of the current item
+            uint32_t ph_q = 0, ph_p = 0, ph_oe = 0, ph_se = 0;
+            auto kv_wait = [&](uint32_t cnt) {
+                mbar_wait(&kv_full[cnt % C::kStages], (cnt / C::kStages) & 1, 200);
+            };
+            auto issue_s = [&](uint32_t st) {              // S_t = Q_t K^T
+                const uint32_t b = skv_addr + st * C::kTileBytes;
+                #pragma unroll
+                for (int k = 0; k < D / 16; ++k) {
+                    const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+                    umma_ss(tS, make_smem_desc(sq_addr + off, 0, 1024), make_smem_desc(b + off, 0, 1024), idesc_s, k > 0);
+                }
+            };
+            auto issue_pv = [&](uint32_t st, bool acc) {   // O_t (+)= P_t V
+                const uint32_t b = skv_addr + st * C::kTileBytes;
+                #pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_ts(tO, tP + k * 8, make_smem_desc(b + k * 2048, 16384, 1024), idesc_pv, acc || k > 0);
+            };
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t slot = it & 1;
+                mbar_wait(&sched_full[slot], (it >> 1) & 1, 201);
+                const int item = sched_item[slot];
+                mbar_arrive(&sched_empty[slot]);
+                if (item >= p.n_items) break;
+                const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
+                const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
+                const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
+                const int n = max(n0, n1), nt = t ? n1 : n0;
+                // ring elements of this item: K(j) = kv_cnt + 2j, V(j) = kv_cnt + 2j + 1
+                auto do_s = [&](int j) {                   // consume K(j): S_t(j) if this tile needs it
+                    const uint32_t cnt = kv_cnt + 2 * j, st = cnt % C::kStages;
+                    kv_wait(cnt);
+                    if (j < nt) {
+                        if (j == 0) { mbar_wait(&q_full[t], ph_q, 202); ph_q ^= 1; }
+                        else if (C::kSepP) { mbar_wait(&s_empty[t], ph_se, 208); ph_se ^= 1; }   // S_t(j-1) is in registers
+                        tc_fence_after();
+                        issue_s(st); tc_commit(&s_full[t]);
+                        if (j == nt - 1) tc_commit(&q_empty[t]);
+                        tc_commit(&kv_empty[st]);
+                    } else {
+                        mbar_arrive(&kv_empty[st]);
+                    }
+                };
+                auto do_pv = [&](int j) {                  // consume V(j): O_t += P_t(j) V(j)
+                    const uint32_t cnt = kv_cnt + 2 * j + 1, st = cnt % C::kStages;
+                    kv_wait(cnt);
+                    if (j < nt) {
+                        mbar_wait(&p_full[t], ph_p, 204); ph_p ^= 1;
+                        if (j == 0) { mbar_wait(&o_empty[t], ph_oe ^ 1, 205); ph_oe ^= 1; }
+                        tc_fence_after();
+                        issue_pv(st, j > 0);
+                        if (C::kSepP) tc_commit(&pv_done[t]);
+                        else if (j == nt - 1) tc_commit(&o_full[t]);
+                        tc_commit(&kv_empty[st]);
+                    } else {
+                        mbar_arrive(&kv_empty[st]);
+                    }
+                };
+                do_s(0);
+                for (int j = 0; j < n; ++j) {
+                    if (C::kSepP) {                        // S_t(j+1) does not depend on P_t(j) V(j): issue it first
+                        if (j + 1 < n) do_s(j + 1);
+                        do_pv(j);
+                    } else {                               // P_t aliases S_t: in-order after P_t(j) V(j)
+                        do_pv(j);
+                        if (j + 1 < n) do_s(j + 1);
+                    }
+                }
+                if (C::kSepP && nt > 0) ph_se ^= 1;        // the arrival for the item's last S_t is never waited on
+                kv_cnt += 2 * n;
+            }
+        }
+        } else {
+        // P_t aliases S_t (TMEM is full at D=128): ONE issuer keeps the strict order P0V, S0, P1V, S1 — interleaving
+        // two tiles' long MMAs at instruction granularity costs tensor throughput (measured 1105 -> 855 TFLOP/s)
+        if (warp == 8) {
         if (lane_id() == 0) {
             constexpr uint32_t idesc_s = make_idesc(kBf16, false, false, 128, 128);
             constexpr uint32_t idesc_pv = make_idesc(kBf16, false, true, 128, D);
             const uint32_t sq_addr = smem_u32(sQ), skv_addr = smem_u32(sKV);
             uint32_t kv_cnt = 0;
             uint32_t ph_q = 0, ph_p = 0, ph_oe = 0;      // bit t = parity to wait for next
-            uint32_t ph_sempty = 0;
             auto kv_wait = [&](uint32_t cnt) {
                 mbar_wait(&kv_full[cnt % C::kStages], (cnt / C::kStages) & 1, 200);
             };
@@ -178,7 +266,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const uint32_t b = skv_addr + st * C::kTileBytes;
                 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_ts(tmem + 256 + t * D, tmem + (C::kSepP ? 384 + t * 64 : t * 128) + k * 8, make_smem_desc(b + k * 2048, 16384, 1024),
+                    umma_ts(tmem + 256 + t * D, tmem + t * 128 + k * 8, make_smem_desc(b + k * 2048, 16384, 1024),
                             idesc_pv, acc || k > 0);
             };
             for (uint32_t it = 0;; ++it) {
@@ -207,48 +295,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     }
                     tc_commit(&kv_empty[st]); ++kv_cnt;
                 }
-                if constexpr (C::kSepP) {
-                    // ring elements of this item: K(j) = base + 2j, V(j) = base + 2j + 1 (K(0) already consumed)
-                    const uint32_t base = kv_cnt - 1;
-                    uint32_t ph_se = ph_sempty;
-                    for (int j = 0; j < n; ++j) {
-                        const uint32_t vcnt = base + 2 * j + 1, kcnt = base + 2 * j + 2;
-                        const uint32_t vst = vcnt % C::kStages, kst = kcnt % C::kStages;
-                        if (j + 1 < n) {                       // S_t(j+1) as soon as S_t(j) is in registers
-                            kv_wait(kcnt);
-                            if (j + 1 < n0) {
-                                mbar_wait(&s_empty[0], ph_se & 1, 208); ph_se ^= 1; tc_fence_after();
-                                issue_s(0, kst); tc_commit(&s_full[0]);
-                                if (j + 1 == n0 - 1) tc_commit(&q_empty[0]);
-                            }
-                            if (j + 1 < n1) {
-                                mbar_wait(&s_empty[1], (ph_se >> 1) & 1, 209); ph_se ^= 2; tc_fence_after();
-                                issue_s(1, kst); tc_commit(&s_full[1]);
-                                if (j + 1 == n1 - 1) tc_commit(&q_empty[1]);
-                            }
-                            tc_commit(&kv_empty[kst]);
-                        }
-                        kv_wait(vcnt);
-                        if (j < n0) {
-                            mbar_wait(&p_full[0], ph_p & 1, 204); ph_p ^= 1;
-                            if (j == 0) { mbar_wait(&o_empty[0], (ph_oe & 1) ^ 1, 205); ph_oe ^= 1; }
-                            tc_fence_after();
-                            issue_pv(0, vst, j > 0); tc_commit(&pv_done[0]);
-                        }
-                        if (j < n1) {
-                            mbar_wait(&p_full[1], (ph_p >> 1) & 1, 206); ph_p ^= 2;
-                            if (j == 0) { mbar_wait(&o_empty[1], ((ph_oe >> 1) & 1) ^ 1, 207); ph_oe ^= 2; }
-                            tc_fence_after();
-                            issue_pv(1, vst, j > 0); tc_commit(&pv_done[1]);
-                        }
-                        tc_commit(&kv_empty[vst]);
-                    }
-                    // the last S_t of the item is never followed by an s_empty wait: skip those phases
-                    if (n0 > 0) ph_se ^= 1;
-                    if (n1 > 0) ph_se ^= 2;
-                    ph_sempty = ph_se;
-                    kv_cnt = base + 2 * n;
-                } else {
                 for (int j = 0; j < n; ++j) {
                         const uint32_t vst = kv_cnt % C::kStages;
                         const uint32_t kst = (kv_cnt + 1) % C::kStages;
@@ -283,8 +329,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                             tc_commit(&kv_empty[kst]); ++kv_cnt;
                         }
                     }
-                }
             }
+        }
+        }
         }
     } else {
         // ================================= softmax warpgroups (0,1) ================================
