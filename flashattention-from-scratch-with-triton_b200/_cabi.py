@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfa_sm100.so")
+# FA_SM100_LIB selects another build of the SAME library (A/B tuning variants); there is still no other backend
+LIB_PATH = os.environ.get("FA_SM100_LIB") or os.path.join(_HERE, "libfa_sm100.so")
 
 # every symbol include/fa_sm100.h declares: name -> (restype, argtypes)
 _vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float

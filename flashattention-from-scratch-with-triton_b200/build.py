@@ -58,6 +58,21 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """A/B builds for tuning: build/variants/libfa_sm100_<name>.so with extra -D flags; select at run time
+    with FA_SM100_LIB=<path> (see _cabi.py)."""
+    out_dir = os.path.join(ROOT, "build", "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libfa_sm100_{name}.so")
+    cmd = [_nvcc(), *ARCH, *COMMON, "-shared", "-Xcompiler", "-fPIC", *[f"-D{d}" for d in defines], "-o", out,
+           os.path.join(CSRC, "fa_api.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"nvcc failed building variant {name}")
+    return out
+
+
 def build_bringup(force: bool = False) -> str:
     os.makedirs(os.path.dirname(BRINGUP), exist_ok=True)
     srcs = [os.path.join(CSRC, "fa_bringup.cu"), os.path.join(CSRC, "fa_ptx.cuh")]
@@ -76,7 +91,11 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--bringup", action="store_true")
     ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("--variant", action="append", default=[], help="name:DEF1=V,DEF2=V  (A/B build)")
     a = ap.parse_args()
+    for v in a.variant:
+        name, _, defs = v.partition(":")
+        print(build_variant(name, [d for d in defs.split(",") if d]))
     print(build_lib(a.force, a.verbose))
     if a.bringup:
         print(build_bringup(a.force))

@@ -35,6 +35,11 @@ struct BwdParams {
     int n_qtiles, n_ktiles;
 };
 
+// Turn-taking between the two math warpgroups around the exp loop (named barriers 3/4, as in the forward):
+// while one warpgroup is on the MUFU unit the other runs its FMA/LDS-heavy dS phase.
+#ifndef FA_BWD_STAGGER
+#define FA_BWD_STAGGER 0   // measured: no gain (both warpgroups share one tile, the MMA wait dominates); kept as a knob
+#endif
 constexpr int kBwdThreads = 384;
 constexpr int kBwdRegsCompute = 208, kBwdRegsOther = 80;
 constexpr float kLog2e = 1.44269504088896340736f;
@@ -289,6 +294,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const uint32_t tDPT = tmem + lane_field + kColDPT + h * 64;
         const int kv_g = jt * 128 + r;
         const float c2 = p.scale_log2;
+        if (FA_BWD_STAGGER && h == 1) named_bar_arrive(3, 256);       // warpgroup A takes the first turn
         for (int it = 0; it < n_it; ++it) {
             const int ss = it % C::kStatStages;
             const uint32_t stat = smem_u32(sStat) + ss * 1024 + h * 256;
@@ -303,14 +309,17 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 uint32_t s[2][32];
                 tmem_ld32(tSTi, s[0]); tmem_ld32(tSTi + 32, s[1]);
                 tc_wait_ld();
+                if (FA_BWD_STAGGER) named_bar_sync(3 + h, 256);
+                const uint64_t c2v = pack_f2(c2, c2);
                 #pragma unroll
                 for (int c = 0; c < 64; c += 4) {
                     const float4 nl = lds128(stat + c * 4);
-                    pv[c]     = ex2_approx(fmaf(__uint_as_float(s[c >> 5][c & 31]),             c2, nl.x));
-                    pv[c + 1] = ex2_approx(fmaf(__uint_as_float(s[(c + 1) >> 5][(c + 1) & 31]), c2, nl.y));
-                    pv[c + 2] = ex2_approx(fmaf(__uint_as_float(s[(c + 2) >> 5][(c + 2) & 31]), c2, nl.z));
-                    pv[c + 3] = ex2_approx(fmaf(__uint_as_float(s[(c + 3) >> 5][(c + 3) & 31]), c2, nl.w));
+                    float x0, x1, x2, x3;
+                    unpack_f2(ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, pack_f2(nl.x, nl.y)), x0, x1);
+                    unpack_f2(ffma2(pack_u2(s[c >> 5][(c & 31) + 2], s[c >> 5][(c & 31) + 3]), c2v, pack_f2(nl.z, nl.w)), x2, x3);
+                    pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1); pv[c + 2] = ex2_approx(x2); pv[c + 3] = ex2_approx(x3);
                 }
+                if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
             }
             if (p.causal && q0 < kv_g) {                 // tile straddles the diagonal: keep q >= kv only
                 const int cmin = kv_g - q0;
@@ -339,10 +348,11 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     for (int i = 0; i < 16; i += 2) {
                         const int c = q * 32 + 2 * i;
                         const float4 dl = lds128(stat + 512 + c * 4);
-                        const float d0 = pv[c] * (__uint_as_float(dp[q][2 * i]) - dl.x);
-                        const float d1 = pv[c + 1] * (__uint_as_float(dp[q][2 * i + 1]) - dl.y);
-                        const float d2 = pv[c + 2] * (__uint_as_float(dp[q][2 * i + 2]) - dl.z);
-                        const float d3 = pv[c + 3] * (__uint_as_float(dp[q][2 * i + 3]) - dl.w);
+                        float d0, d1, d2, d3;        // dS = P o (dP - delta), packed: FADD2 + FMUL2
+                        unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]),
+                                        fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), pack_f2(-dl.x, -dl.y))), d0, d1);
+                        unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]),
+                                        fadd2(pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]), pack_f2(-dl.z, -dl.w))), d2, d3);
                         pk[i] = pack2<kBf16>(d0, d1); pk[i + 1] = pack2<kBf16>(d2, d3);
                     }
                     tmem_st16(tDPT + q * 16, pk);
@@ -485,6 +495,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         const uint32_t tDS = tmem + lane_field + kColDS + h * 32;      // + 64 * (it & 1)
         const int row_g = iq * 128 + r;
         const float c2 = p.scale_log2;
+        if (FA_BWD_STAGGER && h == 1) named_bar_arrive(3, 256);       // warpgroup A takes the first turn
         float nl = -INFINITY, dl = 0.f;
         if (row_g < p.Sq) {
             const float l = p.lse[(size_t)bh * p.Sq + row_g];
@@ -501,8 +512,15 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 tc_wait_ld();
                 tc_fence_before();
                 mbar_arrive(s_empty);
+                if (FA_BWD_STAGGER) named_bar_sync(3 + h, 256);
+                const uint64_t c2v = pack_f2(c2, c2), nlv = pack_f2(nl, nl);
                 #pragma unroll
-                for (int c = 0; c < 64; ++c) pv[c] = ex2_approx(fmaf(__uint_as_float(s[c >> 5][c & 31]), c2, nl));
+                for (int c = 0; c < 64; c += 2) {
+                    float x0, x1;
+                    unpack_f2(ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, nlv), x0, x1);
+                    pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1);
+                }
+                if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
             }
             const int k0 = it * 128 + h * 64;             // global key index of my column 0
             int cmax = p.Sk - 1 - k0;
@@ -523,11 +541,13 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     uint32_t pk[16];
+                    const uint64_t ndl = pack_f2(-dl, -dl);
                     #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int c = q * 32 + 2 * i;
-                        pk[i] = pack2<kBf16>(pv[c] * (__uint_as_float(dp[q][2 * i]) - dl),
-                                             pv[c + 1] * (__uint_as_float(dp[q][2 * i + 1]) - dl));
+                        float d0, d1;
+                        unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), ndl)), d0, d1);
+                        pk[i] = pack2<kBf16>(d0, d1);
                     }
                     tmem_st16(tDS + (it & 1) * 64 + q * 16, pk);
                 }

@@ -47,6 +47,24 @@ template <int D> struct FwdCfg {
 
 constexpr int kFwdThreads = 384;    // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
 constexpr int kFwdRegsSoftmax = 208, kFwdRegsOther = 80;   // setmaxnreg split of the 168 x 384 launch pool
+// Of every FA_FWD_POLY_DEN pairs of exponentials, FA_FWD_POLY_NUM are evaluated on the FMA pipe (ex2_poly2),
+// the rest on the MUFU unit: the exp loop is XU-saturated (profiles/), the polynomial shifts load to FFMA2.
+#ifndef FA_FWD_POLY_NUM
+#define FA_FWD_POLY_NUM 0
+#endif
+#ifndef FA_FWD_POLY_DEN
+#define FA_FWD_POLY_DEN 4
+#endif
+// The two softmax warpgroups do identical work and would otherwise run in lockstep, hitting the MUFU unit
+// at the same time and leaving it idle at the same time.  Turn-taking around the exp loop (named barriers
+// 3 and 4, the FlashAttention-3 "warp scheduler barrier" idea) staggers them: while one warpgroup
+// exponentiates, the other loads / reduces / stores.  Rounds are counted per item as max(n0, n1) so that
+// unequal iteration counts (causal, ragged) cannot deadlock.
+// Measured (A/B on one box): D=64 -7 % time, D=128 +2 % (there the single in-order MMA issuer already offsets the
+// two tiles by one S MMA) -> on only where P has its own region.
+#ifndef FA_FWD_STAGGER
+#define FA_FWD_STAGGER (C::kSepP)
+#endif
 constexpr float kLazyRescaleLog2 = 8.0f;   // rescale O only when the row max grows by > 2^8 in exp2 units
 
 // iterations (128-wide K/V tiles) that tile `t` of the item starting at row q0 must visit
@@ -345,6 +363,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         uint8_t* sOt = sO + t * C::kOStageBytes;
         uint32_t ph_s = 0, ph_o = 0, ph_pv = 0;
         const float c2 = p.scale_log2;
+        if (FA_FWD_STAGGER && t == 1) named_bar_arrive(3, 256);        // warpgroup 0 takes the first turn
         for (uint32_t it = 0;; ++it) {
             const uint32_t slot = it & 1;
             mbar_wait(&sched_full[slot], (it >> 1) & 1, 300);
@@ -355,7 +374,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             const int bh = item / p.n_qblk;
             const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
             const int nt = fwd_tile_iters(q0, t, p.Sq, p.Sk, p.causal);
-            if (nt == 0) continue;
+            const int n_rounds = max(nt, fwd_tile_iters(q0, 1 - t, p.Sq, p.Sk, p.causal));
+            if (nt == 0) {
+                if (FA_FWD_STAGGER) for (int j = 0; j < n_rounds; ++j) { named_bar_sync(3 + t, 256); named_bar_arrive(4 - t, 256); }
+                continue;
+            }
             const int row_g = q0 + t * 128 + r;
             float m = -INFINITY, l = 0.f;
             for (int j = 0; j < nt; ++j) {
@@ -407,24 +430,38 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     }
                 }
                 const float neg_mc = (m == -INFINITY) ? 0.f : -m * c2;
-                float l0 = 0.f, l1 = 0.f;
+                if (FA_FWD_STAGGER) named_bar_sync(3 + t, 256);              // my turn on the exp unit
+                // p = exp2(s*c - m*c): FFMA2 on pairs, two pair-accumulators for the row sum (fp32, before rounding: ref :111)
+                const uint64_t c2v = pack_f2(c2, c2), nmv = pack_f2(neg_mc, neg_mc);
+                uint64_t lA = pack_f2(0.f, 0.f), lB = lA;
                 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t pk[16];
                     #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[q][2 * i]), c2, neg_mc));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[q][2 * i + 1]), c2, neg_mc));
-                        l0 += p0; l1 += p1;                                  // fp32, before rounding (ref :111)
+                        const uint64_t xv = ffma2(pack_u2(s[q][2 * i], s[q][2 * i + 1]), c2v, nmv);
+                        float p0, p1;
+                        if ((i % FA_FWD_POLY_DEN) < FA_FWD_POLY_NUM) {
+                            ex2_poly2(xv, p0, p1);
+                        } else {
+                            float x0, x1; unpack_f2(xv, x0, x1);
+                            p0 = ex2_approx(x0); p1 = ex2_approx(x1);
+                        }
+                        if (i & 1) lB = fadd2(lB, pack_f2(p0, p1)); else lA = fadd2(lA, pack_f2(p0, p1));
                         pk[i] = pack2<kBf16>(p0, p1);
                     }
                     tmem_st16(tP + q * 16, pk);
                 }
-                l += l0 + l1;
+                if (FA_FWD_STAGGER) named_bar_arrive(4 - t, 256);            // hand the turn to the other warpgroup
+                {
+                    float a0, a1; unpack_f2(fadd2(lA, lB), a0, a1);
+                    l += a0 + a1;
+                }
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(&p_full[t]);
             }
+            if (FA_FWD_STAGGER) for (int j = nt; j < n_rounds; ++j) { named_bar_sync(3 + t, 256); named_bar_arrive(4 - t, 256); }
             // ---------------- epilogue: O = o / l, LSE = m*scale + ln(l) ----------------
             if constexpr (C::kSepP) { mbar_wait(&pv_done[t], ph_pv, 302); ph_pv ^= 1; }
             else { mbar_wait(&o_full[t], ph_o, 302); ph_o ^= 1; }

@@ -289,6 +289,44 @@ __device__ __forceinline__ void sts32(uint32_t saddr, float a) {
     asm volatile("st.shared.f32 [%0], %1;" :: "r"(saddr), "f"(a) : "memory");
 }
 
+// packed fp32x2 math (FFMA2 / FADD2 / FMUL2 on sm_100): two elements per issue slot
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ uint64_t pack_u2(uint32_t lo, uint32_t hi) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+// exp2 of a pair on the FMA pipe (MUFU relief, the FlashAttention-4 trick): x = n + f with n = round(x),
+// f in [-0.5, 0.5]; 2^f by a degree-3 near-minimax polynomial (max rel. error 7.5e-5, far below the 16-bit
+// rounding of P); 2^n spliced into the exponent field.  x is clamped at -126 so the splice never wraps.
+__device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
+    float x0, x1; unpack_f2(x, x0, x1);
+    const uint64_t xm = pack_f2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    const uint64_t magic = pack_f2(12582912.f, 12582912.f);              // 1.5 * 2^23: low mantissa bits = round(x)
+    const uint64_t t = fadd2(xm, magic);
+    const uint64_t nf = fadd2(t, pack_f2(-12582912.f, -12582912.f));
+    const uint64_t f = ffma2(nf, pack_f2(-1.f, -1.f), xm);
+    uint64_t p = ffma2(pack_f2(0.055179596f, 0.055179596f), f, pack_f2(0.24261186f, 0.24261186f));
+    p = ffma2(p, f, pack_f2(0.69325954f, 0.69325954f));
+    p = ffma2(p, f, pack_f2(0.99992800f, 0.99992800f));
+    float t0, t1, q0, q1; unpack_f2(t, t0, t1); unpack_f2(p, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 // register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it)
 template <int N> __device__ __forceinline__ void reg_alloc()   { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
@@ -296,6 +334,9 @@ template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("s
 // named barrier over a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
 }  // namespace fa
