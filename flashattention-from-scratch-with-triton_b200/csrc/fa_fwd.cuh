@@ -483,7 +483,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         w[i] = pack2<kBf16>(__uint_as_float(o[e >> 5][e & 31]) * inv_l,
                                             __uint_as_float(o[(e + 1) >> 5][(e + 1) & 31]) * inv_l);
                     }
-                    *reinterpret_cast<uint4*>(sOt + sw128_offset(r, g)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    sts128(smem_u32(sOt) + sw128_offset(r, g), w[0], w[1], w[2], w[3]);
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1 + t, 128);

@@ -165,7 +165,11 @@ def ring_attention_forward(q, k, v, group=None, ops=None):
 
 
 def ring_attention_backward(q, k, v, O, dO, LSE, group=None, ops=None):
-    """Gradients for ring_attention_forward.  Returns (dq, dk, dv) for the local rows, in q.dtype."""
+    """Gradients for ring_attention_forward.  Returns (dq, dk, dv) for the local rows, in q.dtype.
+
+    Two rings run under the compute: the K/V block of the next hop is prefetched while the current hop's
+    kernels run, and the fp32 dK/dV accumulators of the block that just left are in flight to the next rank
+    while this rank already computes its contribution to the following block; they are added on arrival."""
     import torch.distributed as dist
     ops = ops or CudaOps()
     world = dist.get_world_size(group); rank = dist.get_rank(group)
@@ -177,32 +181,41 @@ def ring_attention_backward(q, k, v, O, dO, LSE, group=None, ops=None):
     hi = lambda t: t[:, :, c:].contiguous()
     q_hi, O_hi, dO_hi, L_hi, d_hi = hi(q), hi(O), hi(dO), hi(LSE), hi(delta)
     kv = [k.contiguous(), v.contiguous()]
-    dkv = [torch.zeros(B, H, S2, D, **f32), torch.zeros(B, H, S2, D, **f32)]   # travels with kv
+    dkv = [torch.zeros(B, H, S2, D, **f32), torch.zeros(B, H, S2, D, **f32)]   # accumulators of the visiting block
+    dkv_reqs, dkv_in = [], None
     for s in range(world):
-        reqs, nxt = [], None
+        kv_reqs, nxt = [], None
         if s + 1 < world:
             nxt = [torch.empty_like(kv[0]), torch.empty_like(kv[1])]
-            reqs = _exchange(kv, nxt, group, rank, world)
+            kv_reqs = _exchange(kv, nxt, group, rank, world)
         o = (rank - s) % world
         if o == rank:
             dq, dk, dv = ops.bwd(q, kv[0], kv[1], O, dO, LSE, delta, True)
-            dq_acc += dq.float(); dkv[0] += dk.float(); dkv[1] += dv.float()
+            part = (slice(None), slice(None), slice(0, S2))
+            dq_acc.add_(dq)
         elif o < rank:
             dq, dk, dv = ops.bwd(q, kv[0][:, :, :c].contiguous(), kv[1][:, :, :c].contiguous(), O, dO, LSE, delta, False)
-            dq_acc += dq.float(); dkv[0][:, :, :c] += dk.float(); dkv[1][:, :, :c] += dv.float()
+            part = (slice(None), slice(None), slice(0, c))
+            dq_acc.add_(dq)
         else:
             dq, dk, dv = ops.bwd(q_hi, kv[0], kv[1], O_hi, dO_hi, L_hi, d_hi, False)
-            dq_acc[:, :, c:] += dq.float(); dkv[0] += dk.float(); dkv[1] += dv.float()
-        for r in reqs:
+            part = (slice(None), slice(None), slice(0, S2))
+            dq_acc[:, :, c:].add_(dq)
+        if s > 0:                                             # accumulators of this block, sent by the previous rank
+            for r in dkv_reqs:
+                r.wait()
+            dkv = dkv_in
+        dkv[0][part].add_(dk); dkv[1][part].add_(dv)
+        # pass them on with their block (after the last hop they arrive back at the block's owner)
+        dkv_in = [torch.empty_like(dkv[0]), torch.empty_like(dkv[1])]
+        dkv_reqs = _exchange(dkv, dkv_in, group, rank, world)
+        for r in kv_reqs:
             r.wait()
-        # the gradient accumulators follow their K/V block (after the last hop they return to the owner)
-        nd = [torch.empty_like(dkv[0]), torch.empty_like(dkv[1])]
-        for r in _exchange(dkv, nd, group, rank, world):
-            r.wait()
-        dkv = nd
         if nxt is not None:
             kv = nxt
-    return dq_acc.to(q.dtype), dkv[0].to(q.dtype), dkv[1].to(q.dtype)
+    for r in dkv_reqs:
+        r.wait()
+    return dq_acc.to(q.dtype), dkv_in[0].to(q.dtype), dkv_in[1].to(q.dtype)
 
 
 class RingFlashAttentionFunction(torch.autograd.Function):

@@ -233,3 +233,43 @@ def test_product_path_is_the_cuda_library():
     fa.flash_attention_backward(Q, K, V, O, dO, LSE, False)
     assert cabi.load().fa_sm100_launch_count() - n0 == 4          # fwd, delta, dQ, dKV
     assert cabi.last_hang() is None
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 200, 300, 64), (2, 2, 333, 129, 128), (1, 2, 1, 77, 64), (1, 1, 640, 384, 128)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("causal", [False, True], ids=["full", "causal"])
+def test_no_out_of_bounds_writes(shape, causal):
+    """compute-sanitizer is closed on this pool, so: every output of the C-ABI calls sits between 4 KiB
+    sentinel zones inside one arena; ragged shapes make every kernel run partial tiles (TMA clipping,
+    predicated LSE/delta stores).  Any write outside a tensor's extent flips a sentinel."""
+    import ctypes
+    import flashattn_b200._cabi as cabi
+    lib = cabi.load()
+    B, H, Sq, Sk, D = shape
+    GUARD = 4096
+    sizes = dict(o=B * H * Sq * D * 2, lse=B * H * Sq * 4, dq=B * H * Sq * D * 2, dk=B * H * Sk * D * 2,
+                 dv=B * H * Sk * D * 2, delta=B * H * Sq * 4)
+    offs, cur = {}, GUARD
+    for k, n in sizes.items():
+        offs[k] = cur
+        cur += (n + 255) // 256 * 256 + GUARD
+    arena = torch.full((cur,), 0xA5, dtype=torch.uint8, device="cuda")
+    Q, K, V, dO = (t.cuda() for t in orc.make_inputs(B, H, Sq, Sk, D, torch.bfloat16, seed=9))
+    ptr = lambda k: arena.data_ptr() + offs[k]
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.fa_sm100_fwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), ptr("o"), ptr("lse"), B, H, Sq, Sk, D, 1, int(causal), 0.0, st)
+    assert rc == 0, lib.fa_last_error()
+    rc = lib.fa_sm100_bwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), ptr("o"), dO.data_ptr(), ptr("lse"), ptr("dq"), ptr("dk"),
+                          ptr("dv"), ptr("delta"), B, H, Sq, Sk, D, 1, int(causal), 0.0, st)
+    assert rc == 0, lib.fa_last_error()
+    torch.cuda.synchronize()
+    mask = torch.ones(cur, dtype=torch.bool, device="cuda")
+    for k, n in sizes.items():
+        mask[offs[k]:offs[k] + n] = False
+    assert bool((arena[mask] == 0xA5).all()), "a kernel wrote outside its output tensor"
+    # and the in-bounds results are the right ones
+    O = arena[offs["o"]:offs["o"] + sizes["o"]].view(torch.bfloat16).view(B, H, Sq, D)
+    dK = arena[offs["dk"]:offs["dk"] + sizes["dk"]].view(torch.bfloat16).view(B, H, Sk, D)
+    rO, _, _, rdK, _ = orc.closed_form(Q.cpu(), K.cpu(), V.cpu(), dO.cpu(), causal)
+    assert _close(O.cpu(), rO) and _close(dK.cpu(), rdK)
+    assert cabi.last_hang() is None
