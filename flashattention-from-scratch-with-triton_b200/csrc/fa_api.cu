@@ -225,6 +225,13 @@ int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* 
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;
     p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
+    p.sms = dev->sms;
+    {   // two scheduler counters from the ring, zeroed on the stream ahead of the kernels
+        const unsigned int slot = g_sched_next.fetch_add(2) % (kSchedRing - 1);
+        p.sched_dkv = dev->sched_ring + slot; p.sched_dq = dev->sched_ring + slot + 1;
+        cudaError_t e = cudaMemsetAsync(p.sched_dkv, 0, 2 * sizeof(unsigned int), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(sched)");
+    }
     rc = launch_bwd(mq, mk, mv, mdo, mdq, mdk, mdv, p, D, dtype, parts, st);
     g_launches += ((parts & FA_BWD_DQ) ? 1 : 0) + ((parts & FA_BWD_DKV) ? 1 : 0);
     return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_bwd kernels launch");

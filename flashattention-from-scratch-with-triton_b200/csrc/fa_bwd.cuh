@@ -33,6 +33,9 @@ struct BwdParams {
     const float* lse;      // [BH, Sq]
     const float* delta;    // [BH, Sq]
     int n_qtiles, n_ktiles;
+    unsigned int* sched_dkv;   // work counters (zeroed before launch) for the persistent kernels
+    unsigned int* sched_dq;
+    int sms;
 };
 
 // Turn-taking between the two math warpgroups around the exp loop (named barriers 3/4, as in the forward):
@@ -81,7 +84,7 @@ __device__ __forceinline__ void issue_scores(uint32_t d_tmem, uint32_t a_addr, u
     #pragma unroll
     for (int k = 0; k < D / 16; ++k) {
         const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-        umma_ss(d_tmem, make_smem_desc(a_addr + off, 0, 1024), make_smem_desc(b_addr + off, 0, 1024), idesc, k > 0);
+        umma_ss_e(d_tmem, make_smem_desc(a_addr + off, 0, 1024), make_smem_desc(b_addr + off, 0, 1024), idesc, k > 0);
     }
 }
 // gradient MMA: D[tmem 128 x D] (+)= A[tmem: 128 lanes x 128 16-bit, two 32-column runs at a_tmem and
@@ -92,7 +95,7 @@ __device__ __forceinline__ void issue_grad(uint32_t d_tmem, uint32_t a_tmem, uin
     constexpr uint32_t idesc = make_idesc(kBf16, false, true, 128, D);
     #pragma unroll
     for (int k = 0; k < 8; ++k)
-        umma_ts(d_tmem, a_tmem + (kSplitA ? (k >> 2) * 64 + (k & 3) * 8 : k * 8),
+        umma_ts_e(d_tmem, a_tmem + (kSplitA ? (k >> 2) * 64 + (k & 3) * 8 : k * 8),
                 make_smem_desc(b_addr + k * 2048, 16384, 1024), idesc, acc || k > 0);
 }
 
@@ -122,42 +125,67 @@ __device__ __forceinline__ void stage_grad_half(uint32_t t_acc, uint8_t* stage, 
 }
 
 // =================================================================================================
-// dK / dV
+// dK / dV  — persistent: one CTA per SM walks (b,h, kv-tile) items from a dynamic scheduler; the next item's
+// K/V/Q/dO loads, statistics and first score MMAs run under the current item's epilogue.
 // =================================================================================================
+#ifndef FA_BWD_PERSISTENT
+#define FA_BWD_PERSISTENT 1     // 0: grid = one CTA per item through the same code (A/B switch)
+#endif
+
+template <int D> struct DkvCfg {
+    static constexpr int kChunks = D / 64;
+    static constexpr int kTileBytes = 128 * D * 2;
+    static constexpr int kStages = (D == 128) ? 2 : 4;
+    static constexpr int kStatStages = 8;
+    static constexpr bool kSepStage = (D == 64);          // own dK/dV staging: next K/V can land under the epilogue
+    static constexpr int kOffRes = 0;
+    static constexpr int kOffStage = 2 * kTileBytes;
+    static constexpr int kStageBytes = 2 * kTileBytes;
+    static constexpr int kOffStat = kOffStage + kStages * kStageBytes;
+    static constexpr int kOffOut = kOffStat + kStatStages * 1024;
+    static constexpr int kOffBar = kOffOut + (kSepStage ? 2 * kTileBytes : 0);
+    static constexpr int kNumBars = 16 + 3 * kStages + 2 * kStatStages;
+    static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 32 + 1024;
+};
+
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                   const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                   const __grid_constant__ CUtensorMap mapdK, const __grid_constant__ CUtensorMap mapdV,
                   const BwdParams p) {
-    using C = BwdCfg<D>;
+    using C = DkvCfg<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem + C::kOffRes;
     uint8_t* sV = sK + C::kTileBytes;
     uint8_t* sStage = smem + C::kOffStage;             // per stage: Q_i then dO_i
-    float* sStat = reinterpret_cast<float*>(smem + C::kOffStat);   // per stage: 128 x nlse2, 128 x delta
+    float* sStat = reinterpret_cast<float*>(smem + C::kOffStat);   // per slot: 128 x (-LSE*log2e), 128 x delta
+    uint8_t* sOutV = C::kSepStage ? smem + C::kOffOut : sV;        // dV / dK staging for the TMA store
+    uint8_t* sOutK = C::kSepStage ? smem + C::kOffOut + C::kTileBytes : sK;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
     uint64_t* k_full = bars;            uint64_t* v_full = bars + 1;
     uint64_t* s_full = bars + 2;        uint64_t* dp_full = bars + 3;
     uint64_t* p_full = bars + 4;        uint64_t* ds_full = bars + 5;
     uint64_t* acc_full = bars + 6;      uint64_t* s_full1 = bars + 7;    // second S^T buffer (kDoubleS)
-    uint64_t* q_full = bars + 8;                        // [kStages]
+    uint64_t* acc_empty = bars + 8;     uint64_t* kv_free = bars + 9;
+    uint64_t* sched_full = bars + 10;   uint64_t* sched_empty = bars + 12;   // [2] each
+    uint64_t* q_full = bars + 16;                       // [kStages]
     uint64_t* do_full = q_full + C::kStages;            // [kStages]
     uint64_t* stage_empty = do_full + C::kStages;       // [kStages]
     uint64_t* stat_full = stage_empty + C::kStages;     // [kStatStages]
     uint64_t* stat_empty = stat_full + C::kStatStages;  // [kStatStages]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
+    volatile int* sched_item = reinterpret_cast<volatile int*>(bars + C::kNumBars);   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sched_item) + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int bh = blockIdx.x / p.n_ktiles;
-    const int jt = blockIdx.x % p.n_ktiles;            // ascending kv tile = heavy first under causal
-    const int i_start = p.causal ? jt : 0;             // first Q tile with a row >= kv_block_start (:341)
-    const int n_it = max(p.n_qtiles - i_start, 0);
+    const int n_items = p.BH * p.n_ktiles;
 
     if (tid == 0) {
         mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(s_full1, 1); mbar_init(dp_full, 1);
-        mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1);
+        mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1); mbar_init(acc_empty, 256);
+        mbar_init(kv_free, C::kSepStage ? 1 : 2);         // MMA thread (+ the store's read-done when staging aliases K/V)
+        for (int i = 0; i < 2; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 10); }
         for (int i = 0; i < C::kStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&do_full[i], 1); mbar_init(&stage_empty[i], 1); }
         for (int i = 0; i < C::kStatStages; ++i) { mbar_init(&stat_full[i], 1); mbar_init(&stat_empty[i], 8); }
         fence_barrier_init();
@@ -172,6 +200,22 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     constexpr bool kDoubleS = (D == 64);
     constexpr uint32_t kColST = 0, kColDPT = kDoubleS ? 256 : 128, kColDV = kDoubleS ? 384 : 256, kColDK = kColDV + D;
 
+    // item -> (bh, kv tile, first q tile, number of q tiles); ascending kv tile = heavy first under causal
+    auto decode = [&](int item, int& bh, int& jt, int& i_start, int& n_it) {
+        bh = item / p.n_ktiles; jt = item % p.n_ktiles;
+        i_start = p.causal ? jt : 0;                       // first Q tile with a row >= kv_block_start (:341)
+        n_it = max(p.n_qtiles - i_start, 0);
+    };
+    // consumer side of the scheduler broadcast: a whole warp calls it (lane 0 releases the slot), or one thread alone
+    auto next_item = [&](uint32_t ix, bool solo = false) -> int {
+        const uint32_t slot = ix & 1;
+        mbar_wait(&sched_full[slot], (ix >> 1) & 1, 440);
+        const int item = sched_item[slot];
+        if (!solo) __syncwarp();
+        if (solo) mbar_arrive(&sched_empty[slot]); else mbar_arrive_e(&sched_empty[slot]);
+        return item;
+    };
+
     if (warp == 11) {
         reg_dealloc<kBwdRegsOther>();
     } else if (warp == 10) {
@@ -181,108 +225,143 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         reg_dealloc<kBwdRegsOther>();
         const int lane = lane_id();
         const uint32_t stat_addr = smem_u32(sStat);
-        auto fetch = [&](int it, float (&nl)[4], float (&dl)[4]) {
-            const int q0 = (i_start + it) * 128;
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int row = q0 + lane + u * 32;
-                nl[u] = -INFINITY; dl[u] = 0.f;           // out-of-range query rows: P = exp2(-inf) = 0
-                if (row < p.Sq) {
-                    const float l = __ldg(p.lse + (size_t)bh * p.Sq + row);
-                    nl[u] = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
-                    dl[u] = __ldg(p.delta + (size_t)bh * p.Sq + row);
+        uint32_t gs = 0;
+        for (uint32_t ix = 0;; ++ix) {
+            const int item = next_item(ix);
+            if (item >= n_items) break;
+            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            auto fetch = [&](int it, float (&nl)[4], float (&dl)[4]) {
+                const int q0 = (i_start + it) * 128;
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int row = q0 + lane + u * 32;
+                    nl[u] = -INFINITY; dl[u] = 0.f;       // out-of-range query rows: P = exp2(-inf) = 0
+                    if (row < p.Sq) {
+                        const float l = __ldg(p.lse + (size_t)bh * p.Sq + row);
+                        nl[u] = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+                        dl[u] = __ldg(p.delta + (size_t)bh * p.Sq + row);
+                    }
                 }
+            };
+            float nl_n[4], dl_n[4];
+            if (n_it > 0) fetch(0, nl_n, dl_n);
+            for (int it = 0; it < n_it; ++it, ++gs) {
+                float nl_c[4], dl_c[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) { nl_c[u] = nl_n[u]; dl_c[u] = dl_n[u]; }
+                if (it + 1 < n_it) fetch(it + 1, nl_n, dl_n);
+                const uint32_t ss = gs % C::kStatStages;
+                mbar_wait(&stat_empty[ss], ((gs / C::kStatStages) & 1) ^ 1, 400);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    sts32(stat_addr + ss * 1024 + (lane + u * 32) * 4, nl_c[u]);
+                    sts32(stat_addr + ss * 1024 + 512 + (lane + u * 32) * 4, dl_c[u]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&stat_full[ss]);
             }
-        };
-        float nl_n[4], dl_n[4];
-        if (n_it > 0) fetch(0, nl_n, dl_n);
-        for (int it = 0; it < n_it; ++it) {
-            float nl_c[4], dl_c[4];
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) { nl_c[u] = nl_n[u]; dl_c[u] = dl_n[u]; }
-            if (it + 1 < n_it) fetch(it + 1, nl_n, dl_n);
-            const int ss = it % C::kStatStages;
-            mbar_wait(&stat_empty[ss], ((it / C::kStatStages) & 1) ^ 1, 400);
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                sts32(stat_addr + ss * 1024 + (lane + u * 32) * 4, nl_c[u]);
-                sts32(stat_addr + ss * 1024 + 512 + (lane + u * 32) * 4, dl_c[u]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&stat_full[ss]);
         }
     } else if (warp == 9) {
-        // --------------------------------- TMA producer ---------------------------------
+        // ----------------------------- TMA producer + scheduler -----------------------------
         reg_dealloc<kBwdRegsOther>();
-        if (lane_id() == 0 && n_it > 0) {
-            tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO);
-            mbar_arrive_expect_tx(k_full, C::kTileBytes);
-            #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sK + c * 16384, &mapK, k_full, c * 64, jt * 128, bh);
-            for (int it = 0; it < n_it; ++it) {
-                const int st = it % C::kStages;
-                uint8_t* sQi = sStage + st * C::kStageBytes;
-                uint8_t* sdOi = sQi + C::kTileBytes;
-                const int q0 = (i_start + it) * 128;
-                mbar_wait(&stage_empty[st], ((it / C::kStages) & 1) ^ 1, 410);
-                mbar_arrive_expect_tx(&q_full[st], C::kTileBytes);
-                #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sQi + c * 16384, &mapQ, &q_full[st], c * 64, q0, bh);
-                if (it == 0) {
-                    mbar_arrive_expect_tx(v_full, C::kTileBytes);
+        {   // whole warp, converged
+            if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
+            __syncwarp();
+            uint32_t git = 0, nacc = 0;
+            int item = blockIdx.x;
+            for (uint32_t ix = 0;; ++ix) {
+                const uint32_t slot = ix & 1;
+                mbar_wait(&sched_empty[slot], ((ix >> 1) & 1) ^ 1, 441);
+                sched_item[slot] = item;
+                mbar_arrive_e(&sched_full[slot]);
+                if (item >= n_items) break;
+                int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+                mbar_wait(kv_free, (ix & 1) ^ 1, 442);        // K/V smem of the previous item released
+                if (n_it > 0) {
+                    mbar_arrive_expect_tx_e(k_full, C::kTileBytes);
                     #pragma unroll
-                    for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sV + c * 16384, &mapV, v_full, c * 64, jt * 128, bh);
+                    for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sK + c * 16384, &mapK, k_full, c * 64, jt * 128, bh);
+                    for (int it = 0; it < n_it; ++it, ++git) {
+                        const uint32_t st = git % C::kStages;
+                        uint8_t* sQi = sStage + st * C::kStageBytes;
+                        uint8_t* sdOi = sQi + C::kTileBytes;
+                        const int q0 = (i_start + it) * 128;
+                        mbar_wait(&stage_empty[st], ((git / C::kStages) & 1) ^ 1, 410);
+                        mbar_arrive_expect_tx_e(&q_full[st], C::kTileBytes);
+                        #pragma unroll
+                        for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sQi + c * 16384, &mapQ, &q_full[st], c * 64, q0, bh);
+                        if (it == 0) {
+                            mbar_arrive_expect_tx_e(v_full, C::kTileBytes);
+                            #pragma unroll
+                            for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sV + c * 16384, &mapV, v_full, c * 64, jt * 128, bh);
+                        }
+                        mbar_arrive_expect_tx_e(&do_full[st], C::kTileBytes);
+                        #pragma unroll
+                        for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sdOi + c * 16384, &mapdO, &do_full[st], c * 64, q0, bh);
+                    }
+                    ++nacc;
                 }
-                mbar_arrive_expect_tx(&do_full[st], C::kTileBytes);
-                #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sdOi + c * 16384, &mapdO, &do_full[st], c * 64, q0, bh);
+                if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dkv, 1u) + (int)gridDim.x : n_items;
+                item = __shfl_sync(0xffffffffu, item, 0);
             }
         }
     } else if (warp == 8) {
         // ---------------------------------- MMA issuer ----------------------------------
         reg_dealloc<kBwdRegsOther>();
-        if (lane_id() == 0 && n_it > 0) {
-            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aSt = smem_u32(sStage);
-            mbar_wait(k_full, 0, 420);
-            mbar_wait(&q_full[0], 0, 421); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColST, aK, aSt); tc_commit(s_full);
-            if (kDoubleS && n_it > 1) {
-                mbar_wait(&q_full[1 % C::kStages], 0, 428); tc_fence_after();
-                issue_scores<D, kBf16>(tmem + kColST + 128, aK, aSt + (1 % C::kStages) * C::kStageBytes); tc_commit(s_full1);
+        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aSt = smem_u32(sStage);
+        uint32_t git = 0, gi = 0, nacc = 0;
+        for (uint32_t ix = 0;; ++ix) {           // whole warp, converged
+            const int item = next_item(ix);
+            if (item >= n_items) break;
+            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            auto qfull = [&](uint32_t g) { mbar_wait(&q_full[g % C::kStages], (g / C::kStages) & 1, 421); };
+            auto dofull = [&](uint32_t g) { mbar_wait(&do_full[g % C::kStages], (g / C::kStages) & 1, 423); };
+            auto stage_addr = [&](uint32_t g) { return aSt + (g % C::kStages) * C::kStageBytes; };
+            if (n_it > 0) {
+                mbar_wait(k_full, nacc & 1, 420);
+                qfull(git); tc_fence_after();
+                issue_scores<D, kBf16>(tmem + kColST + (kDoubleS ? (gi & 1) * 128 : 0), aK, stage_addr(git));
+                tc_commit_e((kDoubleS && (gi & 1)) ? s_full1 : s_full);
+                if (kDoubleS && n_it > 1) {
+                    qfull(git + 1); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColST + ((gi + 1) & 1) * 128, aK, stage_addr(git + 1));
+                    tc_commit_e(((gi + 1) & 1) ? s_full1 : s_full);
+                }
+                mbar_wait(v_full, nacc & 1, 422);
+                dofull(git); tc_fence_after();
+                issue_scores<D, kBf16>(tmem + kColDPT, aV, stage_addr(git) + C::kTileBytes); tc_commit_e(dp_full);
             }
-            mbar_wait(v_full, 0, 422);
-            mbar_wait(&do_full[0], 0, 423); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColDPT, aV, aSt + C::kTileBytes); tc_commit(dp_full);
             for (int it = 0; it < n_it; ++it) {
-                const int st = it % C::kStages;
-                const uint32_t aQ = aSt + st * C::kStageBytes, adO = aQ + C::kTileBytes;
+                const uint32_t g = gi + it, gt = git + it;
+                const uint32_t aQ = stage_addr(gt), adO = aQ + C::kTileBytes;
                 const bool more = it + 1 < n_it;
-                const int st1 = (it + 1) % C::kStages;
-                const uint32_t ph1 = ((it + 1) / C::kStages) & 1;
-                const uint32_t aQ1 = aSt + st1 * C::kStageBytes;
-                const uint32_t sbuf = kDoubleS ? (it & 1) * 128 : 0;
-                mbar_wait(p_full, it & 1, 424); tc_fence_after();
+                const uint32_t sbuf = kDoubleS ? (g & 1) * 128 : 0;
+                mbar_wait(p_full, g & 1, 424);
+                if (it == 0) mbar_wait(acc_empty, (ix & 1) ^ 1, 429);     // previous item's dV/dK drained from TMEM
+                tc_fence_after();
                 issue_grad<D, kBf16>(tmem + kColDV, tmem + kColST + sbuf, adO, it > 0);   // dV += P^T dO_i
                 if (kDoubleS) {
                     if (it + 2 < n_it) {                                                   // S^T(i+2) into the buffer dV(i) just read
-                        const int st2 = (it + 2) % C::kStages;
-                        mbar_wait(&q_full[st2], ((it + 2) / C::kStages) & 1, 425); tc_fence_after();
-                        issue_scores<D, kBf16>(tmem + kColST + sbuf, aK, aSt + st2 * C::kStageBytes);
-                        tc_commit((it & 1) ? s_full1 : s_full);
+                        qfull(gt + 2); tc_fence_after();
+                        issue_scores<D, kBf16>(tmem + kColST + sbuf, aK, stage_addr(gt + 2));
+                        tc_commit_e((g & 1) ? s_full1 : s_full);
                     }
                 } else if (more) {
-                    mbar_wait(&q_full[st1], ph1, 425); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColST, aK, aQ1); tc_commit(s_full);     // S^T(i+1)
+                    qfull(gt + 1); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColST, aK, stage_addr(gt + 1)); tc_commit_e(s_full);     // S^T(i+1)
                 }
-                mbar_wait(ds_full, it & 1, 426); tc_fence_after();
+                mbar_wait(ds_full, g & 1, 426); tc_fence_after();
                 issue_grad<D, kBf16>(tmem + kColDK, tmem + kColDPT, aQ, it > 0);           // dK += dS^T Q_i
-                tc_commit(&stage_empty[st]);
+                tc_commit_e(&stage_empty[gt % C::kStages]);
                 if (more) {
-                    mbar_wait(&do_full[st1], ph1, 427); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColDPT, aV, aQ1 + C::kTileBytes); tc_commit(dp_full);   // dP^T(i+1)
+                    dofull(gt + 1); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColDPT, aV, stage_addr(gt + 1) + C::kTileBytes); tc_commit_e(dp_full);   // dP^T(i+1)
                 }
             }
-            tc_commit(acc_full);
+            if (n_it == 0) mbar_wait(acc_empty, (ix & 1) ^ 1, 429);
+            tc_commit_e(acc_full);                       // every MMA of the item is done -> accumulators final
+            tc_commit_e(kv_free);                        // ... and K/V are no longer read
+            gi += n_it; git += n_it; if (n_it > 0) ++nacc;
         }
     } else {
         // ------------------------------- compute warpgroups -------------------------------
@@ -292,92 +371,109 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tST = tmem + lane_field + kColST + h * 64;
         const uint32_t tDPT = tmem + lane_field + kColDPT + h * 64;
-        const int kv_g = jt * 128 + r;
         const float c2 = p.scale_log2;
         if (FA_BWD_STAGGER && h == 1) named_bar_arrive(3, 256);       // warpgroup A takes the first turn
-        for (int it = 0; it < n_it; ++it) {
-            const int ss = it % C::kStatStages;
-            const uint32_t stat = smem_u32(sStat) + ss * 1024 + h * 256;
-            const int q0 = (i_start + it) * 128 + h * 64;       // global query index of my column 0
-            mbar_wait(&stat_full[ss], (it / C::kStatStages) & 1, 430);
-            const uint32_t tSTi = tST + (kDoubleS ? (it & 1) * 128 : 0);
-            if (kDoubleS) mbar_wait((it & 1) ? s_full1 : s_full, (it >> 1) & 1, 431);
-            else mbar_wait(s_full, it & 1, 431);
-            tc_fence_after();
-            float pv[64];
-            {
-                uint32_t s[2][32];
-                tmem_ld32(tSTi, s[0]); tmem_ld32(tSTi + 32, s[1]);
-                tc_wait_ld();
-                if (FA_BWD_STAGGER) named_bar_sync(3 + h, 256);
-                const uint64_t c2v = pack_f2(c2, c2);
-                #pragma unroll
-                for (int c = 0; c < 64; c += 4) {
-                    const float4 nl = lds128(stat + c * 4);
-                    float x0, x1, x2, x3;
-                    unpack_f2(ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, pack_f2(nl.x, nl.y)), x0, x1);
-                    unpack_f2(ffma2(pack_u2(s[c >> 5][(c & 31) + 2], s[c >> 5][(c & 31) + 3]), c2v, pack_f2(nl.z, nl.w)), x2, x3);
-                    pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1); pv[c + 2] = ex2_approx(x2); pv[c + 3] = ex2_approx(x3);
+        uint32_t gi = 0;
+        bool store_pending = false;
+        for (uint32_t ix = 0;; ++ix) {
+            const int item = next_item(ix);
+            if (item >= n_items) break;
+            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            const int kv_g = jt * 128 + r;
+            for (int it = 0; it < n_it; ++it) {
+                const uint32_t g = gi + it;
+                const uint32_t ss = g % C::kStatStages;
+                const uint32_t stat = smem_u32(sStat) + ss * 1024 + h * 256;
+                const int q0 = (i_start + it) * 128 + h * 64;       // global query index of my column 0
+                mbar_wait(&stat_full[ss], (g / C::kStatStages) & 1, 430);
+                const uint32_t tSTi = tST + (kDoubleS ? (g & 1) * 128 : 0);
+                if (kDoubleS) mbar_wait((g & 1) ? s_full1 : s_full, (g >> 1) & 1, 431);
+                else mbar_wait(s_full, g & 1, 431);
+                tc_fence_after();
+                float pv[64];
+                {
+                    uint32_t s[2][32];
+                    tmem_ld32(tSTi, s[0]); tmem_ld32(tSTi + 32, s[1]);
+                    tc_wait_ld();
+                    if (FA_BWD_STAGGER) named_bar_sync(3 + h, 256);
+                    const uint64_t c2v = pack_f2(c2, c2);
+                    #pragma unroll
+                    for (int c = 0; c < 64; c += 4) {
+                        const float4 nl = lds128(stat + c * 4);
+                        float x0, x1, x2, x3;
+                        unpack_f2(ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, pack_f2(nl.x, nl.y)), x0, x1);
+                        unpack_f2(ffma2(pack_u2(s[c >> 5][(c & 31) + 2], s[c >> 5][(c & 31) + 3]), c2v, pack_f2(nl.z, nl.w)), x2, x3);
+                        pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1); pv[c + 2] = ex2_approx(x2); pv[c + 3] = ex2_approx(x3);
+                    }
+                    if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
                 }
-                if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
-            }
-            if (p.causal && q0 < kv_g) {                 // tile straddles the diagonal: keep q >= kv only
-                const int cmin = kv_g - q0;
-                #pragma unroll
-                for (int c = 0; c < 64; ++c) if (c < cmin) pv[c] = 0.f;
-            }
-            #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                uint32_t pk[16];
-                #pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = pack2<kBf16>(pv[q * 32 + 2 * i], pv[q * 32 + 2 * i + 1]);
-                tmem_st16(tSTi + q * 16, pk);
-            }
-            tc_wait_st(); tc_fence_before();
-            mbar_arrive(p_full);
-            mbar_wait(dp_full, it & 1, 432);
-            tc_fence_after();
-            {
-                uint32_t dp[2][32];
-                tmem_ld32(tDPT, dp[0]); tmem_ld32(tDPT + 32, dp[1]);
-                tc_wait_ld();
+                if (p.causal && q0 < kv_g) {                 // tile straddles the diagonal: keep q >= kv only
+                    const int cmin = kv_g - q0;
+                    #pragma unroll
+                    for (int c = 0; c < 64; ++c) if (c < cmin) pv[c] = 0.f;
+                }
                 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     uint32_t pk[16];
                     #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const int c = q * 32 + 2 * i;
-                        const float4 dl = lds128(stat + 512 + c * 4);
-                        float d0, d1, d2, d3;        // dS = P o (dP - delta), packed: FADD2 + FMUL2
-                        unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]),
-                                        fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), pack_f2(-dl.x, -dl.y))), d0, d1);
-                        unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]),
-                                        fadd2(pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]), pack_f2(-dl.z, -dl.w))), d2, d3);
-                        pk[i] = pack2<kBf16>(d0, d1); pk[i + 1] = pack2<kBf16>(d2, d3);
-                    }
-                    tmem_st16(tDPT + q * 16, pk);
+                    for (int i = 0; i < 16; ++i) pk[i] = pack2<kBf16>(pv[q * 32 + 2 * i], pv[q * 32 + 2 * i + 1]);
+                    tmem_st16(tSTi + q * 16, pk);
                 }
+                tc_wait_st(); tc_fence_before();
+                mbar_arrive(p_full);
+                mbar_wait(dp_full, g & 1, 432);
+                tc_fence_after();
+                {
+                    uint32_t dp[2][32];
+                    tmem_ld32(tDPT, dp[0]); tmem_ld32(tDPT + 32, dp[1]);
+                    tc_wait_ld();
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint32_t pk[16];
+                        #pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            const int c = q * 32 + 2 * i;
+                            const float4 dl = lds128(stat + 512 + c * 4);
+                            float d0, d1, d2, d3;        // dS = P o (dP - delta), packed: FADD2 + FMUL2
+                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]),
+                                            fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), pack_f2(-dl.x, -dl.y))), d0, d1);
+                            unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]),
+                                            fadd2(pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]), pack_f2(-dl.z, -dl.w))), d2, d3);
+                            pk[i] = pack2<kBf16>(d0, d1); pk[i + 1] = pack2<kBf16>(d2, d3);
+                        }
+                        tmem_st16(tDPT + q * 16, pk);
+                    }
+                }
+                tc_wait_st(); tc_fence_before();
+                mbar_arrive(ds_full);
+                __syncwarp();
+                if (lane_id() == 0) mbar_arrive(&stat_empty[ss]);    // this warp is done with the slot's statistics
             }
-            tc_wait_st(); tc_fence_before();
-            mbar_arrive(ds_full);
-            __syncwarp();
-            if (lane_id() == 0) mbar_arrive(&stat_empty[ss]);    // this warp is done with the slot's statistics
-        }
-        // epilogue: dV, dK*scale -> 16-bit -> smem (over V, K) -> TMA store
-        if (n_it > 0) { mbar_wait(acc_full, 0, 433); tc_fence_after(); }
-        stage_grad_half<D, kBf16>(tmem + lane_field + kColDV, sV, r, h, 1.0f, n_it == 0);
-        stage_grad_half<D, kBf16>(tmem + lane_field + kColDK, sK, r, h, p.scale, n_it == 0);
-        fence_proxy_async_smem();
-        named_bar_sync(1, 256);
-        if (tid == 0) {
-            #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) {
-                tma_store_3d(&mapdV, sV + c * 16384, c * 64, jt * 128, bh);
-                tma_store_3d(&mapdK, sK + c * 16384, c * 64, jt * 128, bh);
+            gi += n_it;
+            // ---- epilogue: dV, dK*scale -> 16-bit -> smem staging -> TMA store
+            mbar_wait(acc_full, ix & 1, 433); tc_fence_after();
+            if (C::kSepStage) {                              // the previous item's store must have read the staging
+                if (tid == 0 && store_pending) tma_store_wait_read0();
+                named_bar_sync(1, 256);
             }
-            tma_store_commit();
-            tma_store_wait_all0();
+            stage_grad_half<D, kBf16>(tmem + lane_field + kColDV, sOutV, r, h, 1.0f, n_it == 0);
+            stage_grad_half<D, kBf16>(tmem + lane_field + kColDK, sOutK, r, h, p.scale, n_it == 0);
+            tc_fence_before();
+            mbar_arrive(acc_empty);                          // TMEM accumulators drained
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (tid == 0) {
+                #pragma unroll
+                for (int c = 0; c < C::kChunks; ++c) {
+                    tma_store_3d(&mapdV, sOutV + c * 16384, c * 64, jt * 128, bh);
+                    tma_store_3d(&mapdK, sOutK + c * 16384, c * 64, jt * 128, bh);
+                }
+                tma_store_commit();
+                if (!C::kSepStage) { tma_store_wait_read0(); mbar_arrive(kv_free); }   // staging aliases K/V
+            }
+            store_pending = true;
         }
+        if (tid == 0) tma_store_wait_all0();
     }
     tc_fence_before();
     __syncthreads();
@@ -433,57 +529,58 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         reg_dealloc<kBwdRegsOther>();
     } else if (warp == 9) {
         reg_dealloc<kBwdRegsOther>();
-        if (lane_id() == 0) {
-            tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO);
-            mbar_arrive_expect_tx(q_full, C::kTileBytes);
+        {   // whole warp, converged
+            if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
+            __syncwarp();
+            mbar_arrive_expect_tx_e(q_full, C::kTileBytes);
             #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh);
+            for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh);
             for (int it = 0; it < n_it; ++it) {
                 const int ks = it % C::kKStages, vs = it % C::kVStages;
                 uint8_t* sKj = sKr + ks * C::kTileBytes;
                 uint8_t* sVj = sVr + vs * C::kTileBytes;
                 mbar_wait(&k_empty[ks], ((it / C::kKStages) & 1) ^ 1, 510);
-                mbar_arrive_expect_tx(&k_full[ks], C::kTileBytes);
+                mbar_arrive_expect_tx_e(&k_full[ks], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, bh);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, bh);
                 if (it == 0) {
-                    mbar_arrive_expect_tx(do_full, C::kTileBytes);
+                    mbar_arrive_expect_tx_e(do_full, C::kTileBytes);
                     #pragma unroll
-                    for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sdO + c * 16384, &mapdO, do_full, c * 64, iq * 128, bh);
+                    for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sdO + c * 16384, &mapdO, do_full, c * 64, iq * 128, bh);
                 }
                 mbar_wait(&v_empty[vs], ((it / C::kVStages) & 1) ^ 1, 511);
-                mbar_arrive_expect_tx(&v_full[vs], C::kTileBytes);
+                mbar_arrive_expect_tx_e(&v_full[vs], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, bh);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, bh);
             }
         }
     } else if (warp == 8) {
         reg_dealloc<kBwdRegsOther>();
-        if (lane_id() == 0) {
+        {   // whole warp, converged
             const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKr = smem_u32(sKr), aVr = smem_u32(sVr);
             mbar_wait(q_full, 0, 520);
             mbar_wait(&k_full[0], 0, 521); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColS, aQ, aKr); tc_commit(s_full);
+            issue_scores<D, kBf16>(tmem + kColS, aQ, aKr); tc_commit_e(s_full);
             mbar_wait(do_full, 0, 522);
             mbar_wait(&v_full[0], 0, 523); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColDP, adO, aVr); tc_commit(dp_full); tc_commit(&v_empty[0]);
+            issue_scores<D, kBf16>(tmem + kColDP, adO, aVr); tc_commit_e(dp_full); tc_commit_e(&v_empty[0]);
             for (int it = 0; it < n_it; ++it) {
                 const int ks = it % C::kKStages;
                 if (it + 1 < n_it) {
                     const int ks1 = (it + 1) % C::kKStages, vs1 = (it + 1) % C::kVStages;
                     mbar_wait(s_empty, it & 1, 524);               // S(it) is in registers
                     mbar_wait(&k_full[ks1], ((it + 1) / C::kKStages) & 1, 525); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColS, aQ, aKr + ks1 * C::kTileBytes); tc_commit(s_full);     // S(j+1)
+                    issue_scores<D, kBf16>(tmem + kColS, aQ, aKr + ks1 * C::kTileBytes); tc_commit_e(s_full);     // S(j+1)
                     mbar_wait(dp_empty, it & 1, 528);              // dP(it) is in registers
                     mbar_wait(&v_full[vs1], ((it + 1) / C::kVStages) & 1, 527); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColDP, adO, aVr + vs1 * C::kTileBytes); tc_commit(dp_full);  // dP(j+1)
-                    tc_commit(&v_empty[vs1]);
+                    issue_scores<D, kBf16>(tmem + kColDP, adO, aVr + vs1 * C::kTileBytes); tc_commit_e(dp_full);  // dP(j+1)
+                    tc_commit_e(&v_empty[vs1]);
                 }
                 mbar_wait(ds_full, it & 1, 526); tc_fence_after();
                 issue_grad<D, kBf16, false>(tmem + kColDQ, tmem + kColDS + (it & 1) * 64, aKr + ks * C::kTileBytes, it > 0);   // dQ += dS K_j
-                tc_commit(&k_empty[ks]);
+                tc_commit_e(&k_empty[ks]);
             }
-            tc_commit(acc_full);
+            tc_commit_e(acc_full);
         }
     } else {
         reg_alloc<kBwdRegsCompute>();
@@ -577,7 +674,7 @@ int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
                  int parts, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(fa_bwd_dkv_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<D>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(fa_bwd_dkv_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(fa_bwd_dq_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
@@ -589,8 +686,11 @@ int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
-    if (parts & 4)
-        fa_bwd_dkv_kernel<D, kBf16><<<p.BH * p.n_ktiles, kBwdThreads, BwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
+    if (parts & 4) {
+        const int items = p.BH * p.n_ktiles;
+        const int grid = FA_BWD_PERSISTENT ? (items < p.sms ? items : p.sms) : items;
+        fa_bwd_dkv_kernel<D, kBf16><<<grid, kBwdThreads, DkvCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -130,8 +130,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     } else if (warp == 9) {
         // ================================ TMA producer + scheduler ================================
         reg_dealloc<kFwdRegsOther>();
-        if (lane_id() == 0) {
-            tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV);
+        {   // whole warp, converged; single-lane instructions elect their leader (fa_ptx.cuh)
+            if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); }
+            __syncwarp();
             uint32_t kv_cnt = 0;        // K/V tiles produced so far
             uint32_t q_cnt0 = 0, q_cnt1 = 0;
             int item = blockIdx.x;
@@ -139,7 +140,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const uint32_t slot = it & 1;
                 mbar_wait(&sched_empty[slot], ((it >> 1) & 1) ^ 1, 100);
                 sched_item[slot] = item;
-                mbar_arrive(&sched_full[slot]);
+                mbar_arrive_e(&sched_full[slot]);
                 if (item >= p.n_items) break;
                 const int bh = item / p.n_qblk;
                 const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;   // heavy (late) query blocks first
@@ -148,19 +149,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const int n = max(n0, n1);
                 auto load_q = [&](int t, uint32_t& cnt) {
                     mbar_wait(&q_empty[t], (cnt & 1) ^ 1, 101 + t);
-                    mbar_arrive_expect_tx(&q_full[t], C::kTileBytes);
+                    mbar_arrive_expect_tx_e(&q_full[t], C::kTileBytes);
                     #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c)
-                        tma_load_3d(sQ + t * C::kTileBytes + c * 16384, &mapQ, &q_full[t], c * 64, q0 + t * 128, bh);
+                        tma_load_3d_e(sQ + t * C::kTileBytes + c * 16384, &mapQ, &q_full[t], c * 64, q0 + t * 128, bh);
                     ++cnt;
                 };
                 auto load_kv = [&](const CUtensorMap* m, int j) {
                     const uint32_t st = kv_cnt % C::kStages;
                     mbar_wait(&kv_empty[st], ((kv_cnt / C::kStages) & 1) ^ 1, 110);
-                    mbar_arrive_expect_tx(&kv_full[st], C::kTileBytes);
+                    mbar_arrive_expect_tx_e(&kv_full[st], C::kTileBytes);
                     #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c)
-                        tma_load_3d(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, j * 128, bh);
+                        tma_load_3d_e(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, j * 128, bh);
                     ++kv_cnt;
                 };
                 if (n0 > 0) load_q(0, q_cnt0);
@@ -168,7 +169,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 if (n1 > 0) load_q(1, q_cnt1);
                 load_kv(&mapV, 0);
                 for (int j = 1; j < n; ++j) { load_kv(&mapK, j); load_kv(&mapV, j); }
-                item = (int)atomicAdd(p.sched, 1u) + (int)gridDim.x;
+                if (lane_id() == 0) item = (int)atomicAdd(p.sched, 1u) + (int)gridDim.x;
+                item = __shfl_sync(0xffffffffu, item, 0);
             }
         }
     } else if (warp == 8 || warp == 10) {
@@ -178,7 +180,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         // that belongs to the other.  Each K/V ring slot is released by both threads (kv_empty count 2).
         reg_dealloc<kFwdRegsOther>();
         if constexpr (C::kSepP) {
-        if (lane_id() == 0) {
+        {   // whole warp, converged
             const int t = (warp == 8) ? 0 : 1;
             constexpr uint32_t idesc_s = make_idesc(kBf16, false, false, 128, 128);
             constexpr uint32_t idesc_pv = make_idesc(kBf16, false, true, 128, D);
@@ -195,20 +197,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 #pragma unroll
                 for (int k = 0; k < D / 16; ++k) {
                     const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-                    umma_ss(tS, make_smem_desc(sq_addr + off, 0, 1024), make_smem_desc(b + off, 0, 1024), idesc_s, k > 0);
+                    umma_ss_e(tS, make_smem_desc(sq_addr + off, 0, 1024), make_smem_desc(b + off, 0, 1024), idesc_s, k > 0);
                 }
             };
             auto issue_pv = [&](uint32_t st, bool acc) {   // O_t (+)= P_t V
                 const uint32_t b = skv_addr + st * C::kTileBytes;
                 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_ts(tO, tP + k * 8, make_smem_desc(b + k * 2048, 16384, 1024), idesc_pv, acc || k > 0);
+                    umma_ts_e(tO, tP + k * 8, make_smem_desc(b + k * 2048, 16384, 1024), idesc_pv, acc || k > 0);
             };
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it & 1;
                 mbar_wait(&sched_full[slot], (it >> 1) & 1, 201);
                 const int item = sched_item[slot];
-                mbar_arrive(&sched_empty[slot]);
+                mbar_arrive_e(&sched_empty[slot]);
                 if (item >= p.n_items) break;
                 const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
                 const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
@@ -222,11 +224,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         if (j == 0) { mbar_wait(&q_full[t], ph_q, 202); ph_q ^= 1; }
                         else if (C::kSepP) { mbar_wait(&s_empty[t], ph_se, 208); ph_se ^= 1; }   // S_t(j-1) is in registers
                         tc_fence_after();
-                        issue_s(st); tc_commit(&s_full[t]);
-                        if (j == nt - 1) tc_commit(&q_empty[t]);
-                        tc_commit(&kv_empty[st]);
+                        issue_s(st); tc_commit_e(&s_full[t]);
+                        if (j == nt - 1) tc_commit_e(&q_empty[t]);
+                        tc_commit_e(&kv_empty[st]);
                     } else {
-                        mbar_arrive(&kv_empty[st]);
+                        mbar_arrive_e(&kv_empty[st]);
                     }
                 };
                 auto do_pv = [&](int j) {                  // consume V(j): O_t += P_t(j) V(j)
@@ -237,11 +239,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         if (j == 0) { mbar_wait(&o_empty[t], ph_oe ^ 1, 205); ph_oe ^= 1; }
                         tc_fence_after();
                         issue_pv(st, j > 0);
-                        if (C::kSepP) tc_commit(&pv_done[t]);
-                        else if (j == nt - 1) tc_commit(&o_full[t]);
-                        tc_commit(&kv_empty[st]);
+                        if (C::kSepP) tc_commit_e(&pv_done[t]);
+                        else if (j == nt - 1) tc_commit_e(&o_full[t]);
+                        tc_commit_e(&kv_empty[st]);
                     } else {
-                        mbar_arrive(&kv_empty[st]);
+                        mbar_arrive_e(&kv_empty[st]);
                     }
                 };
                 do_s(0);
@@ -262,7 +264,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         // P_t aliases S_t (TMEM is full at D=128): ONE issuer keeps the strict order P0V, S0, P1V, S1 — interleaving
         // two tiles' long MMAs at instruction granularity costs tensor throughput (measured 1105 -> 855 TFLOP/s)
         if (warp == 8) {
-        if (lane_id() == 0) {
+        {   // whole warp, converged
             constexpr uint32_t idesc_s = make_idesc(kBf16, false, false, 128, 128);
             constexpr uint32_t idesc_pv = make_idesc(kBf16, false, true, 128, D);
             const uint32_t sq_addr = smem_u32(sQ), skv_addr = smem_u32(sKV);
@@ -276,7 +278,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 #pragma unroll
                 for (int k = 0; k < D / 16; ++k) {
                     const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-                    umma_ss(tmem + t * 128, make_smem_desc(a + off, 0, 1024), make_smem_desc(b + off, 0, 1024),
+                    umma_ss_e(tmem + t * 128, make_smem_desc(a + off, 0, 1024), make_smem_desc(b + off, 0, 1024),
                             idesc_s, k > 0);
                 }
             };
@@ -284,14 +286,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const uint32_t b = skv_addr + st * C::kTileBytes;
                 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_ts(tmem + 256 + t * D, tmem + t * 128 + k * 8, make_smem_desc(b + k * 2048, 16384, 1024),
+                    umma_ts_e(tmem + 256 + t * D, tmem + t * 128 + k * 8, make_smem_desc(b + k * 2048, 16384, 1024),
                             idesc_pv, acc || k > 0);
             };
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it & 1;
                 mbar_wait(&sched_full[slot], (it >> 1) & 1, 201);
                 const int item = sched_item[slot];
-                mbar_arrive(&sched_empty[slot]);
+                mbar_arrive_e(&sched_empty[slot]);
                 if (item >= p.n_items) break;
                 const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
                 const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
@@ -303,15 +305,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     kv_wait(kv_cnt);
                     if (n0 > 0) {
                         mbar_wait(&q_full[0], ph_q & 1, 202); ph_q ^= 1; tc_fence_after();
-                        issue_s(0, st); tc_commit(&s_full[0]);
-                        if (n0 == 1) tc_commit(&q_empty[0]);
+                        issue_s(0, st); tc_commit_e(&s_full[0]);
+                        if (n0 == 1) tc_commit_e(&q_empty[0]);
                     }
                     if (n1 > 0) {
                         mbar_wait(&q_full[1], (ph_q >> 1) & 1, 203); ph_q ^= 2; tc_fence_after();
-                        issue_s(1, st); tc_commit(&s_full[1]);
-                        if (n1 == 1) tc_commit(&q_empty[1]);
+                        issue_s(1, st); tc_commit_e(&s_full[1]);
+                        if (n1 == 1) tc_commit_e(&q_empty[1]);
                     }
-                    tc_commit(&kv_empty[st]); ++kv_cnt;
+                    tc_commit_e(&kv_empty[st]); ++kv_cnt;
                 }
                 for (int j = 0; j < n; ++j) {
                         const uint32_t vst = kv_cnt % C::kStages;
@@ -323,28 +325,28 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                             if (j == 0) { mbar_wait(&o_empty[0], (ph_oe & 1) ^ 1, 205); ph_oe ^= 1; }
                             tc_fence_after();
                             issue_pv(0, vst, j > 0);
-                            if (j == n0 - 1) tc_commit(&o_full[0]);
+                            if (j == n0 - 1) tc_commit_e(&o_full[0]);
                         }
                         if (more) kv_wait(kv_cnt + 1);         // K(j+1)
                         if (j + 1 < n0) {
                             tc_fence_after();
-                            issue_s(0, kst); tc_commit(&s_full[0]);
-                            if (j + 1 == n0 - 1) tc_commit(&q_empty[0]);
+                            issue_s(0, kst); tc_commit_e(&s_full[0]);
+                            if (j + 1 == n0 - 1) tc_commit_e(&q_empty[0]);
                         }
                         if (j < n1) {
                             mbar_wait(&p_full[1], (ph_p >> 1) & 1, 206); ph_p ^= 2;
                             if (j == 0) { mbar_wait(&o_empty[1], ((ph_oe >> 1) & 1) ^ 1, 207); ph_oe ^= 2; }
                             tc_fence_after();
                             issue_pv(1, vst, j > 0);
-                            if (j == n1 - 1) tc_commit(&o_full[1]);
+                            if (j == n1 - 1) tc_commit_e(&o_full[1]);
                         }
-                        tc_commit(&kv_empty[vst]); ++kv_cnt;
+                        tc_commit_e(&kv_empty[vst]); ++kv_cnt;
                         if (more) {
                             if (j + 1 < n1) {
-                                issue_s(1, kst); tc_commit(&s_full[1]);
-                                if (j + 1 == n1 - 1) tc_commit(&q_empty[1]);
+                                issue_s(1, kst); tc_commit_e(&s_full[1]);
+                                if (j + 1 == n1 - 1) tc_commit_e(&q_empty[1]);
                             }
-                            tc_commit(&kv_empty[kst]); ++kv_cnt;
+                            tc_commit_e(&kv_empty[kst]); ++kv_cnt;
                         }
                     }
             }

@@ -327,6 +327,45 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
     p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
+// One leader lane of a CONVERGED warp.  The MMA / TMA warps keep all 32 lanes in uniform control flow and elect
+// only around the tcgen05 / TMA / arrive instructions: descriptors computed in converged code stay in uniform
+// registers, whereas code inside a divergent `if (lane == 0)` makes ptxas wrap every UTCHMMA / UTMALDG in an
+// ELECT + R2UR.BROADCAST loop (~13 extra instructions per MMA on the latency-critical issue path).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Self-electing variants: every lane of the converged warp calls them, one leader lane executes the instruction.
+#define FA_ELECT_PROLOGUE "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+__device__ __forceinline__ void umma_ss_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(FA_ELECT_PROLOGUE ".reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(FA_ELECT_PROLOGUE ".reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_e(uint64_t* bar) {
+    asm volatile(FA_ELECT_PROLOGUE "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_e(uint64_t* bar) {
+    asm volatile(FA_ELECT_PROLOGUE "@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_e(uint64_t* bar, uint32_t bytes) {
+    asm volatile(FA_ELECT_PROLOGUE "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_e(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(FA_ELECT_PROLOGUE
+                 "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it)
 template <int N> __device__ __forceinline__ void reg_alloc()   { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }

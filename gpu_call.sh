@@ -1,9 +1,11 @@
-mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "out_of_bounds" 2>&1 | tail -3
-for N in 8 4; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N > gpurun_out/c21_bench$N.json 2> gpurun_out/c21_bench$N.err; echo "bench$N rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/c21_bench$N.json')); print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), d['clocks'])"
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$N scripts/bench_multi.py --config C4,C5 > gpurun_out/c21_multi$N.jsonl 2> gpurun_out/c21_multi$N.err; echo "multi$N rc=$?"; cat gpurun_out/c21_multi$N.jsonl | cut -c1-420
-done
-timeout 600 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -2
+mkdir -p gpurun_out; rm -f gpurun_out/c24_ab.jsonl
+timeout 300 python scripts/dev_check.py --what all --cases small,mid,c2 > gpurun_out/c24_check.log 2>&1; echo "check rc=$?"; grep -E "EXCEPTION|hang" gpurun_out/c24_check.log | cut -c1-300; grep -c '"ok": true' gpurun_out/c24_check.log
+for round in 1 2; do for v in old elect; do
+FA_SM100_LIB=$PWD/build/variants/libfa_sm100_$v.so timeout 200 python scripts/ab_time.py all >> gpurun_out/c24_ab.jsonl 2>> gpurun_out/c24_ab.err
+done; done
+python - <<'PY'
+import json
+for l in open('gpurun_out/c24_ab.jsonl'):
+    d=json.loads(l); print(d['lib'][11:-3], {k:(v['fwd'],v['dQ'],v['dKV']) for k,v in d.items() if isinstance(v,dict)})
+PY
+tail -3 gpurun_out/c24_ab.err
