@@ -59,7 +59,7 @@ def _peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
         self.index = index; self.proc = None; self.lines = []
@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.th.start()
@@ -84,20 +84,25 @@ class ClockSampler:
         except Exception:
             pass
         self.th.join(timeout=1)
-        sm, mx, reasons = [], None, set()
+        sm_all, sm_load, mx, reasons = [], [], None, set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                clk = float(f[0]); mx = float(f[1]); util = float(f[6])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+            sm_all.append(clk)
+            if util >= 50:
+                sm_load.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        sm = sorted(sm_load or sm_all)
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm_all), samples_under_load=len(sm_load),
+                    window="1.5 s loop of the same step right after the timed region (100 ms period; median over samples with GPU utilisation >= 50 %)")
 
 
 def cpu_baseline(B, H, S, D, causal, budget_s=20.0):
@@ -259,12 +264,19 @@ def main():
     for _ in range(a.warmup):
         flush.zero_(); step()
     barrier()
-    sampler = ClockSampler(local); sampler.start()
     n0 = lib.fa_sm100_launch_count() if lib else 0
     barrier()
     ts = time_steps(step, a.steps, 0, flush)
     barrier()
     launches = (lib.fa_sm100_launch_count() - n0) if lib else 0
+    # Clocks under load: the timed region of a small workload lasts only milliseconds, far below nvidia-smi's
+    # sampling period, so the SAME step is looped for ~1.5 s right after it while clocks / throttle reasons are sampled.
+    sampler = ClockSampler(local); sampler.start()
+    t_probe = time.time() + 1.5
+    while time.time() < t_probe:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
     clocks = sampler.stop()
     my_ms = sum(ts) / len(ts)
     ms = my_ms
@@ -356,6 +368,7 @@ def main():
                                 ms={k: kb2[k]["ms"] for k in kb2}, note="kernel-only (C-ABI launches, CUDA events), bf16")
                 del q2, k2, v2, do2
             line["also"] = also
+    if rank == 0 and not a.no_extras:
         cb = cpu_baseline(B, H, S, D, causal)
         line["cpu_baseline"] = cb
     if rank == 0:

@@ -62,21 +62,6 @@ template <int D> struct BwdCfg {
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 };
 
-// dQ kernel: Q, dO resident; K_j lives from S(j) to dQ(j) (long), V_j only for dP(j) (short) -> separate rings,
-// K one slot deeper so that the loads keep a full tile of lead over the MMAs.
-template <int D> struct DqCfg {
-    static constexpr int kChunks = D / 64;
-    static constexpr int kTileBytes = 128 * D * 2;
-    static constexpr int kKStages = (D == 128) ? 3 : 4;
-    static constexpr int kVStages = (D == 128) ? 2 : 4;
-    static constexpr int kOffRes = 0;
-    static constexpr int kOffK = 2 * kTileBytes;
-    static constexpr int kOffV = kOffK + kKStages * kTileBytes;
-    static constexpr int kOffBar = kOffV + kVStages * kTileBytes;
-    static constexpr int kNumBars = 8 + 2 * kKStages + 2 * kVStages;
-    static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
-};
-
 // score-tile MMA: D[tmem 128x128] = A[smem 128 x D, K-major] * B[smem 128 x D, K-major]^T
 template <int D, bool kBf16>
 __device__ __forceinline__ void issue_scores(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr) {
@@ -210,8 +195,8 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     auto next_item = [&](uint32_t ix, bool solo = false) -> int {
         const uint32_t slot = ix & 1;
         mbar_wait(&sched_full[slot], (ix >> 1) & 1, 440);
-        const int item = sched_item[slot];
-        if (!solo) __syncwarp();
+        int item = sched_item[slot];
+        if (!solo) item = __shfl_sync(0xffffffffu, item, 0);      // provably warp-uniform -> uniform registers downstream
         if (solo) mbar_arrive(&sched_empty[slot]); else mbar_arrive_e(&sched_empty[slot]);
         return item;
     };
@@ -481,8 +466,25 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
 }
 
 // =================================================================================================
-// dQ
+// dQ — persistent: one CTA per SM walks (b,h, q-tile) items (late = heavy tiles first) from a dynamic scheduler.
 // =================================================================================================
+template <int D> struct DqCfg {
+    static constexpr int kChunks = D / 64;
+    static constexpr int kTileBytes = 128 * D * 2;
+    // Q, dO resident; K_j lives from S(j) to dQ(j) (long), V_j only for dP(j) (short) -> separate rings,
+    // K one slot deeper so that the loads keep a full tile of lead over the MMAs.
+    static constexpr int kKStages = (D == 128) ? 3 : 4;
+    static constexpr int kVStages = (D == 128) ? 2 : 4;
+    static constexpr bool kSepStage = (D == 64);          // own dQ staging: the next item's Q/dO can land under the epilogue
+    static constexpr int kOffRes = 0;
+    static constexpr int kOffK = 2 * kTileBytes;
+    static constexpr int kOffV = kOffK + kKStages * kTileBytes;
+    static constexpr int kOffOut = kOffV + kVStages * kTileBytes;
+    static constexpr int kOffBar = kOffOut + (kSepStage ? kTileBytes : 0);
+    static constexpr int kNumBars = 16 + 2 * kKStages + 2 * kVStages;
+    static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 32 + 1024;
+};
+
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -495,25 +497,30 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     uint8_t* sdO = sQ + C::kTileBytes;
     uint8_t* sKr = smem + C::kOffK;                    // K ring
     uint8_t* sVr = smem + C::kOffV;                    // V ring
+    uint8_t* sOut = C::kSepStage ? smem + C::kOffOut : sQ;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
     uint64_t* q_full = bars;            uint64_t* do_full = bars + 1;
     uint64_t* s_full = bars + 2;        uint64_t* dp_full = bars + 3;
     uint64_t* s_empty = bars + 4;       uint64_t* ds_full = bars + 5;
     uint64_t* acc_full = bars + 6;      uint64_t* dp_empty = bars + 7;
-    uint64_t* k_full = bars + 8;                        // [kKStages]
+    uint64_t* acc_empty = bars + 8;     uint64_t* qdo_free = bars + 9;
+    uint64_t* sched_full = bars + 10;   uint64_t* sched_empty = bars + 12;   // [2] each
+    uint64_t* k_full = bars + 16;                       // [kKStages]
     uint64_t* k_empty = k_full + C::kKStages;           // [kKStages]
     uint64_t* v_full = k_empty + C::kKStages;           // [kVStages]
     uint64_t* v_empty = v_full + C::kVStages;           // [kVStages]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
+    volatile int* sched_item = reinterpret_cast<volatile int*>(bars + C::kNumBars);   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sched_item) + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int bh = blockIdx.x / p.n_qtiles;
-    const int iq = p.n_qtiles - 1 - (blockIdx.x % p.n_qtiles);      // descending q tile = heavy first under causal
-    const int n_it = fwd_tile_iters(iq * 128, 0, p.Sq, p.Sk, p.causal);   // same truncation as forward (:219)
+    const int n_items = p.BH * p.n_qtiles;
 
     if (tid == 0) {
         mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1);
-        mbar_init(s_empty, 256); mbar_init(dp_empty, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1);
+        mbar_init(s_empty, 256); mbar_init(dp_empty, 256); mbar_init(ds_full, 256);
+        mbar_init(acc_full, 1); mbar_init(acc_empty, 256);
+        mbar_init(qdo_free, C::kSepStage ? 1 : 2);        // MMA thread (+ the store's read-done when staging aliases Q)
+        for (int i = 0; i < 2; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 9); }   // MMA warp + 8 math warps
         for (int i = 0; i < C::kKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < C::kVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
         fence_barrier_init();
@@ -523,23 +530,46 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDS = 256 + D;   // dS buffers: kColDS + 64*(j&1)
+    constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDS = 256 + D;   // dS buffers: kColDS + 64*(g&1)
+
+    // item -> (bh, q tile, number of kv tiles); descending q tile = heavy first under causal (:219 truncation)
+    auto decode = [&](int item, int& bh, int& iq, int& n_it) {
+        bh = item / p.n_qtiles; iq = p.n_qtiles - 1 - (item % p.n_qtiles);
+        n_it = fwd_tile_iters(iq * 128, 0, p.Sq, p.Sk, p.causal);
+    };
+    auto next_item = [&](uint32_t ix) -> int {           // whole warp
+        const uint32_t slot = ix & 1;
+        mbar_wait(&sched_full[slot], (ix >> 1) & 1, 540);
+        const int item = __shfl_sync(0xffffffffu, sched_item[slot], 0);   // provably warp-uniform -> uniform registers downstream
+        mbar_arrive_e(&sched_empty[slot]);
+        return item;
+    };
 
     if (warp >= 10) {
         reg_dealloc<kBwdRegsOther>();
     } else if (warp == 9) {
+        // ----------------------------- TMA producer + scheduler (whole warp, converged) -----------------------------
         reg_dealloc<kBwdRegsOther>();
-        {   // whole warp, converged
-            if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
-            __syncwarp();
+        if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
+        __syncwarp();
+        uint32_t g = 0;
+        int item = blockIdx.x;
+        for (uint32_t ix = 0;; ++ix) {
+            const uint32_t slot = ix & 1;
+            mbar_wait(&sched_empty[slot], ((ix >> 1) & 1) ^ 1, 541);
+            sched_item[slot] = item;
+            mbar_arrive_e(&sched_full[slot]);
+            if (item >= n_items) break;
+            int bh, iq, n_it; decode(item, bh, iq, n_it);
+            mbar_wait(qdo_free, (ix & 1) ^ 1, 542);          // Q/dO smem of the previous item released
             mbar_arrive_expect_tx_e(q_full, C::kTileBytes);
             #pragma unroll
             for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh);
-            for (int it = 0; it < n_it; ++it) {
-                const int ks = it % C::kKStages, vs = it % C::kVStages;
+            for (int it = 0; it < n_it; ++it, ++g) {
+                const uint32_t ks = g % C::kKStages, vs = g % C::kVStages;
                 uint8_t* sKj = sKr + ks * C::kTileBytes;
                 uint8_t* sVj = sVr + vs * C::kTileBytes;
-                mbar_wait(&k_empty[ks], ((it / C::kKStages) & 1) ^ 1, 510);
+                mbar_wait(&k_empty[ks], ((g / C::kKStages) & 1) ^ 1, 510);
                 mbar_arrive_expect_tx_e(&k_full[ks], C::kTileBytes);
                 #pragma unroll
                 for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, bh);
@@ -548,39 +578,52 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sdO + c * 16384, &mapdO, do_full, c * 64, iq * 128, bh);
                 }
-                mbar_wait(&v_empty[vs], ((it / C::kVStages) & 1) ^ 1, 511);
+                mbar_wait(&v_empty[vs], ((g / C::kVStages) & 1) ^ 1, 511);
                 mbar_arrive_expect_tx_e(&v_full[vs], C::kTileBytes);
                 #pragma unroll
                 for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, bh);
             }
+            if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dq, 1u) + (int)gridDim.x : n_items;
+            item = __shfl_sync(0xffffffffu, item, 0);
         }
     } else if (warp == 8) {
+        // ---------------------------------- MMA issuer (whole warp, converged) ----------------------------------
         reg_dealloc<kBwdRegsOther>();
-        {   // whole warp, converged
-            const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKr = smem_u32(sKr), aVr = smem_u32(sVr);
-            mbar_wait(q_full, 0, 520);
-            mbar_wait(&k_full[0], 0, 521); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColS, aQ, aKr); tc_commit_e(s_full);
-            mbar_wait(do_full, 0, 522);
-            mbar_wait(&v_full[0], 0, 523); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColDP, adO, aVr); tc_commit_e(dp_full); tc_commit_e(&v_empty[0]);
+        const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKr = smem_u32(sKr), aVr = smem_u32(sVr);
+        uint32_t gi = 0;
+        for (uint32_t ix = 0;; ++ix) {
+            const int item = next_item(ix);
+            if (item >= n_items) break;
+            int bh, iq, n_it; decode(item, bh, iq, n_it);
+            auto kfull = [&](uint32_t g) { mbar_wait(&k_full[g % C::kKStages], (g / C::kKStages) & 1, 521); };
+            auto vfull = [&](uint32_t g) { mbar_wait(&v_full[g % C::kVStages], (g / C::kVStages) & 1, 523); };
+            mbar_wait(q_full, ix & 1, 520);
+            kfull(gi); tc_fence_after();
+            issue_scores<D, kBf16>(tmem + kColS, aQ, aKr + (gi % C::kKStages) * C::kTileBytes); tc_commit_e(s_full);
+            mbar_wait(do_full, ix & 1, 522);
+            vfull(gi); tc_fence_after();
+            issue_scores<D, kBf16>(tmem + kColDP, adO, aVr + (gi % C::kVStages) * C::kTileBytes); tc_commit_e(dp_full);
+            tc_commit_e(&v_empty[gi % C::kVStages]);
             for (int it = 0; it < n_it; ++it) {
-                const int ks = it % C::kKStages;
+                const uint32_t g = gi + it;
                 if (it + 1 < n_it) {
-                    const int ks1 = (it + 1) % C::kKStages, vs1 = (it + 1) % C::kVStages;
-                    mbar_wait(s_empty, it & 1, 524);               // S(it) is in registers
-                    mbar_wait(&k_full[ks1], ((it + 1) / C::kKStages) & 1, 525); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColS, aQ, aKr + ks1 * C::kTileBytes); tc_commit_e(s_full);     // S(j+1)
-                    mbar_wait(dp_empty, it & 1, 528);              // dP(it) is in registers
-                    mbar_wait(&v_full[vs1], ((it + 1) / C::kVStages) & 1, 527); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColDP, adO, aVr + vs1 * C::kTileBytes); tc_commit_e(dp_full);  // dP(j+1)
-                    tc_commit_e(&v_empty[vs1]);
+                    mbar_wait(s_empty, g & 1, 524);                // S(j) is in registers
+                    kfull(g + 1); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColS, aQ, aKr + ((g + 1) % C::kKStages) * C::kTileBytes); tc_commit_e(s_full);     // S(j+1)
+                    mbar_wait(dp_empty, g & 1, 528);               // dP(j) is in registers
+                    vfull(g + 1); tc_fence_after();
+                    issue_scores<D, kBf16>(tmem + kColDP, adO, aVr + ((g + 1) % C::kVStages) * C::kTileBytes); tc_commit_e(dp_full);  // dP(j+1)
+                    tc_commit_e(&v_empty[(g + 1) % C::kVStages]);
                 }
-                mbar_wait(ds_full, it & 1, 526); tc_fence_after();
-                issue_grad<D, kBf16, false>(tmem + kColDQ, tmem + kColDS + (it & 1) * 64, aKr + ks * C::kTileBytes, it > 0);   // dQ += dS K_j
-                tc_commit_e(&k_empty[ks]);
+                mbar_wait(ds_full, g & 1, 526);
+                if (it == 0) mbar_wait(acc_empty, (ix & 1) ^ 1, 529);     // previous item's dQ drained from TMEM
+                tc_fence_after();
+                issue_grad<D, kBf16, false>(tmem + kColDQ, tmem + kColDS + (g & 1) * 64, aKr + (g % C::kKStages) * C::kTileBytes, it > 0);   // dQ += dS K_j
+                tc_commit_e(&k_empty[g % C::kKStages]);
             }
-            tc_commit_e(acc_full);
+            tc_commit_e(acc_full);                     // every MMA of the item is done -> dQ final
+            tc_commit_e(qdo_free);                     // ... and Q/dO are no longer read
+            gi += n_it;
         }
     } else {
         reg_alloc<kBwdRegsCompute>();
@@ -589,79 +632,97 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem + lane_field + kColS + h * 64;
         const uint32_t tDP = tmem + lane_field + kColDP + h * 64;
-        const uint32_t tDS = tmem + lane_field + kColDS + h * 32;      // + 64 * (it & 1)
-        const int row_g = iq * 128 + r;
+        const uint32_t tDS = tmem + lane_field + kColDS + h * 32;      // + 64 * (g & 1)
         const float c2 = p.scale_log2;
         if (FA_BWD_STAGGER && h == 1) named_bar_arrive(3, 256);       // warpgroup A takes the first turn
-        float nl = -INFINITY, dl = 0.f;
-        if (row_g < p.Sq) {
-            const float l = p.lse[(size_t)bh * p.Sq + row_g];
-            nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
-            dl = p.delta[(size_t)bh * p.Sq + row_g];
-        }
-        for (int it = 0; it < n_it; ++it) {
-            mbar_wait(s_full, it & 1, 530);
-            tc_fence_after();
-            float pv[64];
-            {
-                uint32_t s[2][32];
-                tmem_ld32(tS, s[0]); tmem_ld32(tS + 32, s[1]);
-                tc_wait_ld();
-                tc_fence_before();
-                mbar_arrive(s_empty);
-                if (FA_BWD_STAGGER) named_bar_sync(3 + h, 256);
-                const uint64_t c2v = pack_f2(c2, c2), nlv = pack_f2(nl, nl);
-                #pragma unroll
-                for (int c = 0; c < 64; c += 2) {
-                    float x0, x1;
-                    unpack_f2(ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, nlv), x0, x1);
-                    pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1);
-                }
-                if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
+        uint32_t gi = 0;
+        bool store_pending = false;
+        for (uint32_t ix = 0;; ++ix) {
+            const int item = next_item(ix);
+            if (item >= n_items) break;
+            int bh, iq, n_it; decode(item, bh, iq, n_it);
+            const int row_g = iq * 128 + r;
+            float nl = -INFINITY, dl = 0.f;
+            if (row_g < p.Sq) {
+                const float l = __ldg(p.lse + (size_t)bh * p.Sq + row_g);
+                nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+                dl = __ldg(p.delta + (size_t)bh * p.Sq + row_g);
             }
-            const int k0 = it * 128 + h * 64;             // global key index of my column 0
-            int cmax = p.Sk - 1 - k0;
-            if (p.causal) cmax = min(cmax, row_g - k0);
-            if (cmax < 63) {
-                #pragma unroll
-                for (int c = 0; c < 64; ++c) if (c > cmax) pv[c] = 0.f;
-            }
-            mbar_wait(dp_full, it & 1, 531);
-            tc_fence_after();
-            {
-                uint32_t dp[2][32];
-                tmem_ld32(tDP, dp[0]); tmem_ld32(tDP + 32, dp[1]);
-                tc_wait_ld();
-                tc_fence_before();
-                mbar_arrive(dp_empty);
-                // dS(it) goes to buffer it&1; its previous reader dQ(it-2) completed before dp_full(it) fired
-                #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    uint32_t pk[16];
-                    const uint64_t ndl = pack_f2(-dl, -dl);
+            for (int it = 0; it < n_it; ++it) {
+                const uint32_t g = gi + it;
+                mbar_wait(s_full, g & 1, 530);
+                tc_fence_after();
+                float pv[64];
+                {
+                    uint32_t s[2][32];
+                    tmem_ld32(tS, s[0]); tmem_ld32(tS + 32, s[1]);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(s_empty);
+                    if (FA_BWD_STAGGER) named_bar_sync(3 + h, 256);
+                    const uint64_t c2v = pack_f2(c2, c2), nlv = pack_f2(nl, nl);
                     #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int c = q * 32 + 2 * i;
-                        float d0, d1;
-                        unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), ndl)), d0, d1);
-                        pk[i] = pack2<kBf16>(d0, d1);
+                    for (int c = 0; c < 64; c += 2) {
+                        float x0, x1;
+                        unpack_f2(ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, nlv), x0, x1);
+                        pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1);
                     }
-                    tmem_st16(tDS + (it & 1) * 64 + q * 16, pk);
+                    if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
                 }
+                const int k0 = it * 128 + h * 64;             // global key index of my column 0
+                int cmax = p.Sk - 1 - k0;
+                if (p.causal) cmax = min(cmax, row_g - k0);
+                if (cmax < 63) {
+                    #pragma unroll
+                    for (int c = 0; c < 64; ++c) if (c > cmax) pv[c] = 0.f;
+                }
+                mbar_wait(dp_full, g & 1, 531);
+                tc_fence_after();
+                {
+                    uint32_t dp[2][32];
+                    tmem_ld32(tDP, dp[0]); tmem_ld32(tDP + 32, dp[1]);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(dp_empty);
+                    // dS(g) goes to buffer g&1; its previous reader dQ(g-2) completed before dp_full(g) fired
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint32_t pk[16];
+                        const uint64_t ndl = pack_f2(-dl, -dl);
+                        #pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int c = q * 32 + 2 * i;
+                            float d0, d1;
+                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), ndl)), d0, d1);
+                            pk[i] = pack2<kBf16>(d0, d1);
+                        }
+                        tmem_st16(tDS + (g & 1) * 64 + q * 16, pk);
+                    }
+                }
+                tc_wait_st(); tc_fence_before();
+                mbar_arrive(ds_full);
             }
-            tc_wait_st(); tc_fence_before();
-            mbar_arrive(ds_full);
+            gi += n_it;
+            // ---- epilogue: dQ*scale -> 16-bit -> smem staging -> TMA store
+            mbar_wait(acc_full, ix & 1, 532); tc_fence_after();
+            if (C::kSepStage) {                              // the previous item's store must have read the staging
+                if (tid == 0 && store_pending) tma_store_wait_read0();
+                named_bar_sync(1, 256);
+            }
+            stage_grad_half<D, kBf16>(tmem + lane_field + kColDQ, sOut, r, h, p.scale, false);
+            tc_fence_before();
+            mbar_arrive(acc_empty);                          // dQ drained from TMEM
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (tid == 0) {
+                #pragma unroll
+                for (int c = 0; c < C::kChunks; ++c) tma_store_3d(&mapdQ, sOut + c * 16384, c * 64, iq * 128, bh);
+                tma_store_commit();
+                if (!C::kSepStage) { tma_store_wait_read0(); mbar_arrive(qdo_free); }   // staging aliases Q
+            }
+            store_pending = true;
         }
-        mbar_wait(acc_full, 0, 532); tc_fence_after();
-        stage_grad_half<D, kBf16>(tmem + lane_field + kColDQ, sQ, r, h, p.scale, false);
-        fence_proxy_async_smem();
-        named_bar_sync(1, 256);
-        if (tid == 0) {
-            #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) tma_store_3d(&mapdQ, sQ + c * 16384, c * 64, iq * 128, bh);
-            tma_store_commit();
-            tma_store_wait_all0();
-        }
+        if (tid == 0) tma_store_wait_all0();
     }
     tc_fence_before();
     __syncthreads();
@@ -682,7 +743,9 @@ int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
     }
     // same order as the reference launcher (code/My_FlashAttention_optimized.py:111-126): dQ, then dK/dV
     if (parts & 2) {
-        fa_bwd_dq_kernel<D, kBf16><<<p.BH * p.n_qtiles, kBwdThreads, DqCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
+        const int items = p.BH * p.n_qtiles;
+        const int grid = FA_BWD_PERSISTENT ? (items < p.sms ? items : p.sms) : items;
+        fa_bwd_dq_kernel<D, kBf16><<<grid, kBwdThreads, DqCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }

@@ -209,7 +209,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it & 1;
                 mbar_wait(&sched_full[slot], (it >> 1) & 1, 201);
-                const int item = sched_item[slot];
+                const int item = __shfl_sync(0xffffffffu, sched_item[slot], 0);   // warp-uniform for the compiler
                 mbar_arrive_e(&sched_empty[slot]);
                 if (item >= p.n_items) break;
                 const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
@@ -292,7 +292,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it & 1;
                 mbar_wait(&sched_full[slot], (it >> 1) & 1, 201);
-                const int item = sched_item[slot];
+                const int item = __shfl_sync(0xffffffffu, sched_item[slot], 0);   // warp-uniform for the compiler
                 mbar_arrive_e(&sched_empty[slot]);
                 if (item >= p.n_items) break;
                 const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;

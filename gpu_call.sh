@@ -1,11 +1,14 @@
-mkdir -p gpurun_out; rm -f gpurun_out/c24_ab.jsonl
-timeout 300 python scripts/dev_check.py --what all --cases small,mid,c2 > gpurun_out/c24_check.log 2>&1; echo "check rc=$?"; grep -E "EXCEPTION|hang" gpurun_out/c24_check.log | cut -c1-300; grep -c '"ok": true' gpurun_out/c24_check.log
-for round in 1 2; do for v in old elect; do
-FA_SM100_LIB=$PWD/build/variants/libfa_sm100_$v.so timeout 200 python scripts/ab_time.py all >> gpurun_out/c24_ab.jsonl 2>> gpurun_out/c24_ab.err
-done; done
-python - <<'PY'
-import json
-for l in open('gpurun_out/c24_ab.jsonl'):
-    d=json.loads(l); print(d['lib'][11:-3], {k:(v['fwd'],v['dQ'],v['dKV']) for k,v in d.items() if isinstance(v,dict)})
-PY
-tail -3 gpurun_out/c24_ab.err
+mkdir -p gpurun_out
+timeout 300 python bench.py --steps 10 > gpurun_out/c29_bench.json 2> gpurun_out/c29_bench.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/c29_bench.json')); print(d['value'], d['clocks'])"
+CMD="python bench.py --steps 2 --warmup 3 --no-extras"
+$CMD > gpurun_out/c29_plain_c2.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/c29_launches_c2.csv $CMD > gpurun_out/c29_ncu1.log 2>&1
+echo "launch list rc=$?"
+$CMD > gpurun_out/c29_plain_c2b.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:fa_ -s 12 -c 4 -f -o gpurun_out/c29_prof_c2 $CMD > gpurun_out/c29_ncu2.log 2>&1
+echo "full c2 rc=$?"
+CMD3="python bench.py --steps 2 --warmup 3 --no-extras --workload C3"
+$CMD3 > gpurun_out/c29_plain_c3.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:fa_ -s 12 -c 4 -f -o gpurun_out/c29_prof_c3 $CMD3 > gpurun_out/c29_ncu3.log 2>&1
+echo "full c3 rc=$?"
