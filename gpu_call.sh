@@ -1,14 +1,7 @@
 mkdir -p gpurun_out
-timeout 300 python bench.py --steps 10 > gpurun_out/c29_bench.json 2> gpurun_out/c29_bench.err; echo "bench rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/c29_bench.json')); print(d['value'], d['clocks'])"
-CMD="python bench.py --steps 2 --warmup 3 --no-extras"
-$CMD > gpurun_out/c29_plain_c2.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/c29_launches_c2.csv $CMD > gpurun_out/c29_ncu1.log 2>&1
-echo "launch list rc=$?"
-$CMD > gpurun_out/c29_plain_c2b.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fa_ -s 12 -c 4 -f -o gpurun_out/c29_prof_c2 $CMD > gpurun_out/c29_ncu2.log 2>&1
-echo "full c2 rc=$?"
-CMD3="python bench.py --steps 2 --warmup 3 --no-extras --workload C3"
-$CMD3 > gpurun_out/c29_plain_c3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fa_ -s 12 -c 4 -f -o gpurun_out/c29_prof_c3 $CMD3 > gpurun_out/c29_ncu3.log 2>&1
-echo "full c3 rc=$?"
+N=8
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N > gpurun_out/c31_bench$N.json 2> gpurun_out/c31_bench$N.err; echo "bench$N rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/c31_bench$N.json')); print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), d['clocks']['sm_mhz'], d['clocks']['reasons'])"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 scripts/bench_multi.py --config C4,C5 > gpurun_out/c31_multi$N.jsonl 2> gpurun_out/c31_multi$N.err; echo "multi$N rc=$?"; cut -c1-330 gpurun_out/c31_multi$N.jsonl
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus $N --impl reference > gpurun_out/c31_bench${N}_ref.json 2> /dev/null; echo "ref$N rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/c31_bench${N}_ref.json')); print('ref', d['n_gpus'], round(d['value'],1), 'e2e', round(d['e2e']['value'],1))"
