@@ -41,21 +41,34 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// [BH, S, D] 16-bit tensor viewed as a 3-D map (never flattened across heads, so a partial tile
-// cannot touch the next head — fixes the reference's flattened-descriptor overrun).
-// Box = [1][box_rows][64 columns], SWIZZLE_128B; out-of-range rows read as zero and are not written.
-bool make_map(CUtensorMap* m, const void* ptr, int BH, int S, int D, int dtype, int box_rows) {
+// [B, H, S, D] 16-bit tensor as a 4-D map with explicit batch / head / row strides (never flattened across heads,
+// so a partial tile cannot touch the next head — fixes the reference's flattened-descriptor overrun).
+// Box = [1][1][box_rows][64 columns], SWIZZLE_128B; out-of-range rows read as zero and are not written.
+bool make_map(CUtensorMap* m, const void* ptr, int B, int H, int S, int D, const RowStrides& st, int dtype, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)BH};
-    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)S * D * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)st.r * 2, (cuuint64_t)st.h * 2, (cuuint64_t)st.b * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, dtype == FA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                     3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+// strides of tensor `i` from the caller's array (NULL = contiguous [B,H,S,D]); size-1 dims get a harmless stride
+RowStrides get_strides(const long long* strides, int i, int H, int S, int D) {
+    RowStrides st{(long long)H * S * D, (long long)S * D, (long long)D};
+    if (strides) { st.b = strides[3 * i]; st.h = strides[3 * i + 1]; st.r = strides[3 * i + 2]; }
+    return st;
+}
+bool strides_ok(RowStrides& st, int B, int H, int S, int D) {
+    if (S == 1) st.r = D;                       // TMA wants non-zero 16-byte-multiple strides even for extent-1 dims
+    if (H == 1) st.h = (long long)S * st.r;
+    if (B == 1) st.b = (long long)H * st.h;
+    return st.b > 0 && st.h > 0 && st.r >= D && (st.b % 8 == 0) && (st.h % 8 == 0) && (st.r % 8 == 0);
 }
 
 struct DeviceInfo { int sms = 0; int cc_major = 0; unsigned int* sched_ring = nullptr; };
@@ -139,17 +152,27 @@ int fa_sm100_last_hang(unsigned int out[4]) {
 
 int fa_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                  int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale, void* stream) {
+    return fa_sm100_fwd_strided(q, k, v, o, lse, B, H, Sq, Sk, D, dtype, causal, sm_scale, nullptr, stream);
+}
+
+int fa_sm100_fwd_strided(const void* q, const void* k, const void* v, void* o, float* lse,
+                         int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                         const long long* strides, void* stream) {
     if (!q || !k || !v || !o || !lse) return fail(FA_ERR_NULL, "null tensor pointer");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return fail(FA_ERR_ALIGN, "q/k/v/o must be 16-byte aligned");
+    RowStrides sq = get_strides(strides, 0, H, Sq, D), sk = get_strides(strides, 1, H, Sk, D),
+               sv = get_strides(strides, 2, H, Sk, D), so = get_strides(strides, 3, H, Sq, D);
+    if (!strides_ok(sq, B, H, Sq, D) || !strides_ok(sk, B, H, Sk, D) || !strides_ok(sv, B, H, Sk, D) || !strides_ok(so, B, H, Sq, D))
+        return fail(FA_ERR_STRIDE, "strides must be positive multiples of 8 elements with D contiguous");
     DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
     const int BH = B * H;
     CUtensorMap mq, mk, mv, mo;
-    if (!make_map(&mq, q, BH, Sq, D, dtype, 128) || !make_map(&mk, k, BH, Sk, D, dtype, 128) ||
-        !make_map(&mv, v, BH, Sk, D, dtype, 128) || !make_map(&mo, o, BH, Sq, D, dtype, 128))
-        return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (BH=%d Sq=%d Sk=%d D=%d)", BH, Sq, Sk, D);
+    if (!make_map(&mq, q, B, H, Sq, D, sq, dtype, 128) || !make_map(&mk, k, B, H, Sk, D, sk, dtype, 128) ||
+        !make_map(&mv, v, B, H, Sk, D, sv, dtype, 128) || !make_map(&mo, o, B, H, Sq, D, so, dtype, 128))
+        return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (B=%d H=%d Sq=%d Sk=%d D=%d)", B, H, Sq, Sk, D);
     FwdParams p;
-    p.BH = BH; p.Sq = Sq; p.Sk = Sk;
+    p.BH = BH; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.n_qblk = (Sq + 255) / 256;
     p.n_items = BH * p.n_qblk;
     p.causal = causal ? 1 : 0;
@@ -170,7 +193,8 @@ int fa_sm100_delta(const void* o, const void* dout, float* delta, int B, int H, 
     if (int rc = check_common(B, H, Sq, 1, D, dtype)) return rc;
     if (!aligned16(o) || !aligned16(dout)) return fail(FA_ERR_ALIGN, "o/dout must be 16-byte aligned");
     DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
-    int rc = launch_delta(o, dout, delta, (long long)B * H * Sq, D, dtype, dev->sms, (cudaStream_t)stream);
+    RowStrides sc = get_strides(nullptr, 0, H, Sq, D);
+    int rc = launch_delta(o, dout, delta, (long long)B * H * Sq, H, Sq, sc, sc, D, dtype, dev->sms, (cudaStream_t)stream);
     ++g_launches;
     return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_delta_kernel launch");
 }
@@ -198,29 +222,45 @@ int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* 
                        const float* lse, void* dq, void* dk, void* dv, float* delta,
                        int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale, void* stream,
                        int parts) {
+    return fa_sm100_bwd_strided(q, k, v, o, dout, lse, dq, dk, dv, delta, B, H, Sq, Sk, D, dtype, causal, sm_scale,
+                                nullptr, stream, parts);
+}
+
+int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                         const float* lse, void* dq, void* dk, void* dv, float* delta,
+                         int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                         const long long* strides, void* stream, int parts) {
     if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta) return fail(FA_ERR_NULL, "null tensor pointer");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dout) ||
         !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || !aligned16(lse) || !aligned16(delta))
         return fail(FA_ERR_ALIGN, "all tensors must be 16-byte aligned");
+    RowStrides s_q = get_strides(strides, 0, H, Sq, D), s_k = get_strides(strides, 1, H, Sk, D),
+               s_v = get_strides(strides, 2, H, Sk, D), s_o = get_strides(strides, 3, H, Sq, D),
+               s_do = get_strides(strides, 4, H, Sq, D), s_dq = get_strides(strides, 5, H, Sq, D),
+               s_dk = get_strides(strides, 6, H, Sk, D), s_dv = get_strides(strides, 7, H, Sk, D);
+    if (!strides_ok(s_q, B, H, Sq, D) || !strides_ok(s_k, B, H, Sk, D) || !strides_ok(s_v, B, H, Sk, D) ||
+        !strides_ok(s_o, B, H, Sq, D) || !strides_ok(s_do, B, H, Sq, D) || !strides_ok(s_dq, B, H, Sq, D) ||
+        !strides_ok(s_dk, B, H, Sk, D) || !strides_ok(s_dv, B, H, Sk, D))
+        return fail(FA_ERR_STRIDE, "strides must be positive multiples of 8 elements with D contiguous");
     DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int BH = B * H;
     int rc = 0;
     if (parts & FA_BWD_DELTA) {
-        rc = launch_delta(o, dout, delta, (long long)BH * Sq, D, dtype, dev->sms, st);
+        rc = launch_delta(o, dout, delta, (long long)BH * Sq, H, Sq, s_o, s_do, D, dtype, dev->sms, st);
         ++g_launches;
         if (rc) return cuda_fail((cudaError_t)rc, "fa_delta_kernel launch");
     }
     if (!(parts & (FA_BWD_DQ | FA_BWD_DKV))) return 0;
     CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
-    if (!make_map(&mq, q, BH, Sq, D, dtype, 128) || !make_map(&mk, k, BH, Sk, D, dtype, 128) ||
-        !make_map(&mv, v, BH, Sk, D, dtype, 128) || !make_map(&mdo, dout, BH, Sq, D, dtype, 128) ||
-        !make_map(&mdq, dq, BH, Sq, D, dtype, 128) || !make_map(&mdk, dk, BH, Sk, D, dtype, 128) ||
-        !make_map(&mdv, dv, BH, Sk, D, dtype, 128))
-        return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (BH=%d Sq=%d Sk=%d D=%d)", BH, Sq, Sk, D);
+    if (!make_map(&mq, q, B, H, Sq, D, s_q, dtype, 128) || !make_map(&mk, k, B, H, Sk, D, s_k, dtype, 128) ||
+        !make_map(&mv, v, B, H, Sk, D, s_v, dtype, 128) || !make_map(&mdo, dout, B, H, Sq, D, s_do, dtype, 128) ||
+        !make_map(&mdq, dq, B, H, Sq, D, s_dq, dtype, 128) || !make_map(&mdk, dk, B, H, Sk, D, s_dk, dtype, 128) ||
+        !make_map(&mdv, dv, B, H, Sk, D, s_dv, dtype, 128))
+        return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (B=%d H=%d Sq=%d Sk=%d D=%d)", B, H, Sq, Sk, D);
     BwdParams p;
-    p.BH = BH; p.Sq = Sq; p.Sk = Sk; p.causal = causal ? 1 : 0;
+    p.BH = BH; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal ? 1 : 0;
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;

@@ -28,15 +28,20 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 }
 
 // delta[row] = sum_d fp32(dO[row,d]) * fp32(O[row,d])
+// Element strides (batch, head, row) of a [B,H,S,D] tensor whose D is contiguous
+struct RowStrides { long long b, h, r; };
+
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(256) fa_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ dout,
-                                                       float* __restrict__ delta, long long rows) {
+                                                       float* __restrict__ delta, long long rows, int H, int Sq,
+                                                       RowStrides so, RowStrides sd) {
     constexpr int TPR = D / 8;                       // threads per row
     constexpr int RPB = 256 / TPR;                   // rows per block per step
     const int sub = threadIdx.x % TPR;
     for (long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row < rows; row += (long long)gridDim.x * RPB) {
-        const uint4 a = __ldg(o + row * TPR + sub);
-        const uint4 b = __ldg(dout + row * TPR + sub);
+        const long long bh = row / Sq, sq = row % Sq, bb = bh / H, hh = bh % H;
+        const uint4 a = __ldg(o + ((bb * so.b + hh * so.h + sq * so.r) >> 3) + sub);
+        const uint4 b = __ldg(dout + ((bb * sd.b + hh * sd.h + sq * sd.r) >> 3) + sub);
         float fa_[8], fb[8];
         unpack8<kBf16>(a, fa_); unpack8<kBf16>(b, fb);
         float acc = 0.f;
@@ -48,17 +53,17 @@ __global__ void __launch_bounds__(256) fa_delta_kernel(const uint4* __restrict__
     }
 }
 
-inline int launch_delta(const void* o, const void* dout, float* delta, long long rows, int D, int dtype,
-                        int sms, cudaStream_t st) {
+inline int launch_delta(const void* o, const void* dout, float* delta, long long rows, int H, int Sq, RowStrides so,
+                        RowStrides sd, int D, int dtype, int sms, cudaStream_t st) {
     const int rpb = 256 / (D / 8);
     long long blocks = (rows + rpb - 1) / rpb;
     const long long cap = (long long)sms * 16;
     if (blocks > cap) blocks = cap;
     const uint4* o4 = (const uint4*)o; const uint4* d4 = (const uint4*)dout;
-    if (D == 64) { if (dtype) fa_delta_kernel<64, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows);
-                   else fa_delta_kernel<64, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows); }
-    else         { if (dtype) fa_delta_kernel<128, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows);
-                   else fa_delta_kernel<128, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows); }
+    if (D == 64) { if (dtype) fa_delta_kernel<64, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd);
+                   else fa_delta_kernel<64, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd); }
+    else         { if (dtype) fa_delta_kernel<128, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd);
+                   else fa_delta_kernel<128, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd); }
     return (int)cudaGetLastError();
 }
 

@@ -28,7 +28,7 @@
 namespace fa {
 
 struct BwdParams {
-    int BH, Sq, Sk, causal;
+    int BH, H, Sq, Sk, causal;     // 4-D tensor maps [B, H, S, D]: coordinates (col, row, h, b)
     float scale, scale_log2;
     const float* lse;      // [BH, Sq]
     const float* delta;    // [BH, Sq]
@@ -265,7 +265,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 if (n_it > 0) {
                     mbar_arrive_expect_tx_e(k_full, C::kTileBytes);
                     #pragma unroll
-                    for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sK + c * 16384, &mapK, k_full, c * 64, jt * 128, bh);
+                    for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sK + c * 16384, &mapK, k_full, c * 64, jt * 128, bh % p.H, bh / p.H);
                     for (int it = 0; it < n_it; ++it, ++git) {
                         const uint32_t st = git % C::kStages;
                         uint8_t* sQi = sStage + st * C::kStageBytes;
@@ -274,15 +274,15 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                         mbar_wait(&stage_empty[st], ((git / C::kStages) & 1) ^ 1, 410);
                         mbar_arrive_expect_tx_e(&q_full[st], C::kTileBytes);
                         #pragma unroll
-                        for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sQi + c * 16384, &mapQ, &q_full[st], c * 64, q0, bh);
+                        for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sQi + c * 16384, &mapQ, &q_full[st], c * 64, q0, bh % p.H, bh / p.H);
                         if (it == 0) {
                             mbar_arrive_expect_tx_e(v_full, C::kTileBytes);
                             #pragma unroll
-                            for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sV + c * 16384, &mapV, v_full, c * 64, jt * 128, bh);
+                            for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sV + c * 16384, &mapV, v_full, c * 64, jt * 128, bh % p.H, bh / p.H);
                         }
                         mbar_arrive_expect_tx_e(&do_full[st], C::kTileBytes);
                         #pragma unroll
-                        for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sdOi + c * 16384, &mapdO, &do_full[st], c * 64, q0, bh);
+                        for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sdOi + c * 16384, &mapdO, &do_full[st], c * 64, q0, bh % p.H, bh / p.H);
                     }
                     ++nacc;
                 }
@@ -450,8 +450,8 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             if (tid == 0) {
                 #pragma unroll
                 for (int c = 0; c < C::kChunks; ++c) {
-                    tma_store_3d(&mapdV, sOutV + c * 16384, c * 64, jt * 128, bh);
-                    tma_store_3d(&mapdK, sOutK + c * 16384, c * 64, jt * 128, bh);
+                    tma_store_4d(&mapdV, sOutV + c * 16384, c * 64, jt * 128, bh % p.H, bh / p.H);
+                    tma_store_4d(&mapdK, sOutK + c * 16384, c * 64, jt * 128, bh % p.H, bh / p.H);
                 }
                 tma_store_commit();
                 if (!C::kSepStage) { tma_store_wait_read0(); mbar_arrive(kv_free); }   // staging aliases K/V
@@ -564,7 +564,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             mbar_wait(qdo_free, (ix & 1) ^ 1, 542);          // Q/dO smem of the previous item released
             mbar_arrive_expect_tx_e(q_full, C::kTileBytes);
             #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh);
+            for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh % p.H, bh / p.H);
             for (int it = 0; it < n_it; ++it, ++g) {
                 const uint32_t ks = g % C::kKStages, vs = g % C::kVStages;
                 uint8_t* sKj = sKr + ks * C::kTileBytes;
@@ -572,16 +572,16 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 mbar_wait(&k_empty[ks], ((g / C::kKStages) & 1) ^ 1, 510);
                 mbar_arrive_expect_tx_e(&k_full[ks], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, bh);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, bh % p.H, bh / p.H);
                 if (it == 0) {
                     mbar_arrive_expect_tx_e(do_full, C::kTileBytes);
                     #pragma unroll
-                    for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sdO + c * 16384, &mapdO, do_full, c * 64, iq * 128, bh);
+                    for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sdO + c * 16384, &mapdO, do_full, c * 64, iq * 128, bh % p.H, bh / p.H);
                 }
                 mbar_wait(&v_empty[vs], ((g / C::kVStages) & 1) ^ 1, 511);
                 mbar_arrive_expect_tx_e(&v_full[vs], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_3d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, bh);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, bh % p.H, bh / p.H);
             }
             if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dq, 1u) + (int)gridDim.x : n_items;
             item = __shfl_sync(0xffffffffu, item, 0);
@@ -716,7 +716,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             named_bar_sync(1, 256);
             if (tid == 0) {
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_store_3d(&mapdQ, sOut + c * 16384, c * 64, iq * 128, bh);
+                for (int c = 0; c < C::kChunks; ++c) tma_store_4d(&mapdQ, sOut + c * 16384, c * 64, iq * 128, bh % p.H, bh / p.H);
                 tma_store_commit();
                 if (!C::kSepStage) { tma_store_wait_read0(); mbar_arrive(qdo_free); }   // staging aliases Q
             }

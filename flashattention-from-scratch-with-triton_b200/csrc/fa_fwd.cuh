@@ -21,7 +21,7 @@
 namespace fa {
 
 struct FwdParams {
-    int BH, Sq, Sk;
+    int BH, H, Sq, Sk;     // tensor maps are 4-D [B, H, S, D] with explicit strides: coordinates (col, row, h, b)
     int n_qblk;            // ceil(Sq / 256)
     int n_items;           // BH * n_qblk
     int causal;
@@ -152,7 +152,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     mbar_arrive_expect_tx_e(&q_full[t], C::kTileBytes);
                     #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c)
-                        tma_load_3d_e(sQ + t * C::kTileBytes + c * 16384, &mapQ, &q_full[t], c * 64, q0 + t * 128, bh);
+                        tma_load_4d_e(sQ + t * C::kTileBytes + c * 16384, &mapQ, &q_full[t], c * 64, q0 + t * 128, bh % p.H, bh / p.H);
                     ++cnt;
                 };
                 auto load_kv = [&](const CUtensorMap* m, int j) {
@@ -161,7 +161,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     mbar_arrive_expect_tx_e(&kv_full[st], C::kTileBytes);
                     #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c)
-                        tma_load_3d_e(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, j * 128, bh);
+                        tma_load_4d_e(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, j * 128, bh % p.H, bh / p.H);
                     ++kv_cnt;
                 };
                 if (n0 > 0) load_q(0, q_cnt0);
@@ -490,7 +490,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 fence_proxy_async_smem();
                 named_bar_sync(1 + t, 128);
                 if (r == 0) {
-                    tma_store_3d(&mapO, sOt, c * 64, q0 + t * 128, bh);
+                    tma_store_4d(&mapO, sOt, c * 64, q0 + t * 128, bh % p.H, bh / p.H);
                     tma_store_commit();
                     tma_store_wait_read0();
                 }

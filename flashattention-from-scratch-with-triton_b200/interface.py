@@ -25,21 +25,49 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def tma_compatible(t: torch.Tensor) -> bool:
+    """True if a [B,H,S,D] tensor can be addressed by the kernels' 4-D tensor maps as it is: D contiguous,
+    every other stride a multiple of 8 elements (16 bytes) for dims of extent > 1, 16-byte aligned base."""
+    if t.ndim != 4 or t.stride(3) != 1 or t.data_ptr() % 16:
+        return False
+    return all(t.shape[i] == 1 or (t.stride(i) > 0 and t.stride(i) % 8 == 0) for i in range(3)) and \
+        (t.shape[2] == 1 or t.stride(2) >= t.shape[3])
+
+
+def as_kernel_layout(t: torch.Tensor) -> torch.Tensor:
+    """The reference always calls .contiguous() (code/My_FlashAttention_optimized.py:138-140, :156); here a
+    strided view (e.g. a [B,H,S,D] transpose of a [B,S,H,D] projection output) is used in place, and only
+    layouts the TMA cannot express are copied."""
+    return t if tma_compatible(t) else t.contiguous()
+
+
+def _strides(*tensors):
+    import ctypes
+    arr = (ctypes.c_longlong * (3 * len(tensors)))()
+    for i, t in enumerate(tensors):
+        arr[3 * i], arr[3 * i + 1], arr[3 * i + 2] = t.stride(0), t.stride(1), t.stride(2)
+    return arr
+
+
 def flash_attention_forward(Q, K, V, is_causal, sm_scale=None):
     """Allocate O / LSE and launch the forward kernel (reference :14-60).
 
-    Q: [B,H,S_q,D], K,V: [B,H,S_k,D] contiguous CUDA fp16/bf16.  Returns (O [B,H,S_q,D] in the
-    input dtype, LSE [B,H,S_q] fp32 = max + ln(sum exp) of the scaled scores)."""
+    Q: [B,H,S_q,D], K,V: [B,H,S_k,D] CUDA fp16/bf16, contiguous or TMA-compatible strided views.  Returns
+    (O [B,H,S_q,D] in the input dtype and in Q's memory layout, LSE [B,H,S_q] fp32 = max + ln(sum exp) of the
+    scaled scores)."""
     lib = _cabi.load()
     B, H, S_q, D = Q.shape
     _, _, S_k, _ = K.shape
-    O = torch.empty((B, H, S_q, D), dtype=Q.dtype, device=Q.device)
+    O = torch.empty_like(Q)                               # contiguous Q -> contiguous O (reference :23); else Q's layout
+    if not tma_compatible(O):
+        O = torch.empty((B, H, S_q, D), dtype=Q.dtype, device=Q.device)
     LSE = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
+    st = _strides(Q, K, V, O)
     with torch.cuda.device(Q.device):
-        rc = lib.fa_sm100_fwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), LSE.data_ptr(),
-                              B, H, S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
-                              float(sm_scale) if sm_scale is not None else 0.0, _stream(Q))
-    _cabi.check("fa_sm100_fwd", rc)
+        rc = lib.fa_sm100_fwd_strided(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), LSE.data_ptr(),
+                                      B, H, S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                      float(sm_scale) if sm_scale is not None else 0.0, st, _stream(Q))
+    _cabi.check("fa_sm100_fwd_strided", rc)
     return O, LSE
 
 
@@ -47,33 +75,30 @@ BWD_DELTA, BWD_DQ, BWD_DKV = 1, 2, 4
 
 
 def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, parts, sm_scale=None):
-    """Launch a subset of the backward kernels into caller-provided outputs (per-kernel timing)."""
+    """Launch a subset of the backward kernels into caller-provided outputs (per-kernel timing, ring hops)."""
     lib = _cabi.load()
     B, H, S_q, D = Q.shape
     S_k = K.shape[2]
+    st = _strides(Q, K, V, O, dO, dQ, dK, dV)
     with torch.cuda.device(Q.device):
-        rc = lib.fa_sm100_bwd_parts(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
-                                    LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
-                                    B, H, S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
-                                    float(sm_scale) if sm_scale is not None else 0.0, _stream(Q), int(parts))
-    _cabi.check("fa_sm100_bwd_parts", rc)
+        rc = lib.fa_sm100_bwd_strided(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
+                                      LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
+                                      B, H, S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                      float(sm_scale) if sm_scale is not None else 0.0, st, _stream(Q), int(parts))
+    _cabi.check("fa_sm100_bwd_strided", rc)
+
+
+def _empty_like_kernel(t):
+    e = torch.empty_like(t)
+    return e if tma_compatible(e) else torch.empty(t.shape, dtype=t.dtype, device=t.device)
 
 
 def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None):
     """Allocate dQ / dK / dV (+ fp32 delta) and launch the backward kernels (reference :62-128)."""
-    lib = _cabi.load()
     B, H, S_q, D = Q.shape
-    _, _, S_k, _ = K.shape
-    dQ = torch.empty((B, H, S_q, D), dtype=Q.dtype, device=Q.device)
-    dK = torch.empty((B, H, S_k, D), dtype=Q.dtype, device=Q.device)
-    dV = torch.empty((B, H, S_k, D), dtype=Q.dtype, device=Q.device)
+    dQ, dK, dV = _empty_like_kernel(Q), _empty_like_kernel(K), _empty_like_kernel(V)      # reference :71-73
     delta = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
-    with torch.cuda.device(Q.device):
-        rc = lib.fa_sm100_bwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
-                              LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
-                              B, H, S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
-                              float(sm_scale) if sm_scale is not None else 0.0, _stream(Q))
-    _cabi.check("fa_sm100_bwd", rc)
+    flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, BWD_DELTA | BWD_DQ | BWD_DKV, sm_scale)
     return dQ, dK, dV
 
 
@@ -87,7 +112,7 @@ class FlashAttentionFunction(torch.autograd.Function):
         assert Q.shape[-1] == K.shape[-1] == V.shape[-1]                   # :135
         assert Q.ndim == 4 and K.ndim == 4 and V.ndim == 4                 # :136
         assert K.dtype == Q.dtype and V.dtype == Q.dtype
-        Q_ = Q.contiguous(); K_ = K.contiguous(); V_ = V.contiguous()      # :138-140
+        Q_ = as_kernel_layout(Q); K_ = as_kernel_layout(K); V_ = as_kernel_layout(V)   # :138-140, without needless copies
         O, LSE = flash_attention_forward(Q_, K_, V_, is_causal, sm_scale)
         ctx.save_for_backward(Q_, K_, V_, O, LSE)                          # :145 (same set, same order)
         ctx.is_causal = is_causal                                          # :147
@@ -97,7 +122,7 @@ class FlashAttentionFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dO):
         Q, K, V, O, LSE = ctx.saved_tensors                                # :154
-        dO_ = dO.contiguous()                                              # :156
+        dO_ = as_kernel_layout(dO)                                         # :156
         dQ, dK, dV = flash_attention_backward(Q, K, V, O, dO_, LSE, ctx.is_causal, ctx.sm_scale)
         return dQ, dK, dV, None, None                                      # :166 (+None for sm_scale)
 
@@ -108,6 +133,13 @@ def flash_attention(Q, K, V, is_causal=False, *, sm_scale=None):
 
 
 attention = flash_attention
+
+
+def flash_attention_bshd(q, k, v, is_causal=False, *, sm_scale=None):
+    """Same operator for the [B, S, H, D] layout a fused QKV projection produces: zero-copy in and out
+    (the kernels address the buffers through strided tensor maps).  Returns O as [B, S_q, H, D]."""
+    O = flash_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal, sm_scale=sm_scale)
+    return O.transpose(1, 2)
 
 
 def flash_attention_delta(O, dO):

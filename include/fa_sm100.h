@@ -54,6 +54,21 @@ int fa_sm100_bwd(const void* q, const void* k, const void* v, const void* o, con
                  int B, int H, int Sq, int Sk, int D, int dtype, int causal,
                  float sm_scale, void* stream);
 
+/* Strided variants (what the caller's side of the operator needs): each 16-bit tensor may have
+ * arbitrary batch / head / row strides as long as D is contiguous, every stride is a multiple of 8 elements
+ * (16 bytes) and the base is 16-byte aligned — e.g. [B,H,S,D] views of a [B,S,H,D] buffer coming straight out of
+ * a QKV projection, without the .contiguous() copy the reference makes (code/My_FlashAttention_optimized.py:138-140).
+ * `strides` holds 3 element strides {batch, head, row} per tensor, in the order q,k,v,o (fwd) and
+ * q,k,v,o,dout,dq,dk,dv (bwd); NULL means all contiguous.  lse and delta stay contiguous [B,H,Sq] fp32. */
+int fa_sm100_fwd_strided(const void* q, const void* k, const void* v, void* o, float* lse,
+                         int B, int H, int Sq, int Sk, int D, int dtype, int causal,
+                         float sm_scale, const long long* strides, void* stream);
+int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                         const float* lse, void* dq, void* dk, void* dv, float* delta,
+                         int B, int H, int Sq, int Sk, int D, int dtype, int causal,
+                         float sm_scale, const long long* strides, void* stream, int parts);
+#define FA_ERR_STRIDE (-8)    /* a stride is not a multiple of 8 elements or is negative */
+
 /* Same as fa_sm100_bwd but launches only the selected kernels: parts is a bit mask of
  * FA_BWD_DELTA (1), FA_BWD_DQ (2), FA_BWD_DKV (4).  dQ and dKV read `delta`, so it must have been
  * produced already when FA_BWD_DELTA is not set.  Used to time each kernel on its own (bench.py). */

@@ -18,7 +18,7 @@ def _declared():
 
 def test_header_declares_expected_entry_points():
     d = _declared()
-    for name in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_bwd_parts", "fa_sm100_delta", "fa_sm100_merge", "fa_sm100_supported",
+    for name in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_bwd_parts", "fa_sm100_fwd_strided", "fa_sm100_bwd_strided", "fa_sm100_delta", "fa_sm100_merge", "fa_sm100_supported",
                  "fa_last_error", "fa_sm100_version", "fa_sm100_launch_count", "fa_sm100_last_hang"):
         assert name in d
 
@@ -53,6 +53,9 @@ def test_argument_validation_without_gpu(lib):
     assert bwd(D=32) == -3
     assert bwd(dt=-1) == -2
     assert bwd(dq=p + 8) == -5
+    import ctypes
+    bad = (ctypes.c_longlong * 12)(*([128 * 64 * 2, 128 * 64, 64] * 3 + [128 * 64 * 2, 128 * 64, 60]))   # o row stride 60: not 16-byte
+    assert lib.fa_sm100_fwd_strided(p, p, p, p, p, 1, 2, 128, 128, 64, 1, 0, 0.0, bad, None) == -8
     assert lib.fa_sm100_delta(p, None, p, 1, 1, 128, 64, 1, None) == -1
     assert lib.fa_sm100_merge(p, p, p, None, 1, 1, 128, 64, 1, 128, 0, None) == -1
     assert lib.fa_sm100_merge(p, p, p, p, 1, 1, 128, 64, 1, 128, 64, None) == -4

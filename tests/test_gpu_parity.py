@@ -273,3 +273,32 @@ def test_no_out_of_bounds_writes(shape, causal):
     rO, _, _, rdK, _ = orc.closed_form(Q.cpu(), K.cpu(), V.cpu(), dO.cpu(), causal)
     assert _close(O.cpu(), rO) and _close(dK.cpu(), rdK)
     assert cabi.last_hang() is None
+
+
+@pytest.mark.parametrize("causal", [False, True], ids=["full", "causal"])
+@pytest.mark.parametrize("D", [64, 128])
+def test_bshd_strided_inputs_zero_copy(D, causal):
+    """[B,S,H,D]-layout buffers (what a fused QKV projection produces) go through strided tensor maps: same
+    numbers as the contiguous path (bitwise), no .contiguous() copy, outputs and grads in the caller's layout."""
+    B, S, H = 2, 384, 3
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.randn(B, S, 3, H, D, device="cuda", generator=g).bfloat16()        # packed projection output
+    q, k, v = (qkv[:, :, i].requires_grad_(True) for i in range(3))                # [B,S,H,D] views, row stride 3*H*D
+    dO = torch.randn(B, S, H, D, device="cuda", generator=g).bfloat16()
+    assert fa.tma_compatible(q.transpose(1, 2)) and not q.transpose(1, 2).is_contiguous()
+    O = fa.flash_attention_bshd(q, k, v, causal)
+    assert O.shape == (B, S, H, D)
+    O.backward(dO)
+    qc, kc, vc = (t.detach().transpose(1, 2).contiguous().requires_grad_(True) for t in (q, k, v))
+    Oc = fa.flash_attention(qc, kc, vc, causal)
+    Oc.backward(dO.transpose(1, 2).contiguous())
+    assert torch.equal(O.transpose(1, 2), Oc)
+    for a, b in ((q.grad, qc.grad), (k.grad, kc.grad), (v.grad, vc.grad)):
+        assert torch.equal(a.transpose(1, 2), b)
+    rO, _, rdQ, _, _ = orc.closed_form(qc.detach().cpu(), kc.detach().cpu(), vc.detach().cpu(), dO.transpose(1, 2).cpu(), causal)
+    assert _close(Oc.detach().cpu(), rO) and _close(qc.grad.cpu(), rdQ)
+    # a layout the TMA cannot express (row stride not a multiple of 8 elements) falls back to the reference's copy
+    odd = torch.randn(1, 2, 128, D + 4, device="cuda").bfloat16()[..., :D]
+    assert not fa.tma_compatible(odd)
+    assert _close(fa.flash_attention(odd, odd, odd, causal).cpu(),
+                  orc.closed_form(odd.cpu(), odd.cpu(), odd.cpu(), None, causal)[0])
