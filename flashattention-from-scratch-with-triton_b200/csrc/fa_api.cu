@@ -152,27 +152,28 @@ int fa_sm100_last_hang(unsigned int out[4]) {
 
 int fa_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                  int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale, void* stream) {
-    return fa_sm100_fwd_strided(q, k, v, o, lse, B, H, Sq, Sk, D, dtype, causal, sm_scale, nullptr, stream);
+    return fa_sm100_fwd_strided(q, k, v, o, lse, B, H, H, Sq, Sk, D, dtype, causal, sm_scale, nullptr, stream);
 }
 
 int fa_sm100_fwd_strided(const void* q, const void* k, const void* v, void* o, float* lse,
-                         int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                         int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                          const long long* strides, void* stream) {
     if (!q || !k || !v || !o || !lse) return fail(FA_ERR_NULL, "null tensor pointer");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
+    if (Hk <= 0 || H % Hk) return fail(FA_ERR_SHAPE, "K/V heads %d must divide query heads %d", Hk, H);
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return fail(FA_ERR_ALIGN, "q/k/v/o must be 16-byte aligned");
-    RowStrides sq = get_strides(strides, 0, H, Sq, D), sk = get_strides(strides, 1, H, Sk, D),
-               sv = get_strides(strides, 2, H, Sk, D), so = get_strides(strides, 3, H, Sq, D);
-    if (!strides_ok(sq, B, H, Sq, D) || !strides_ok(sk, B, H, Sk, D) || !strides_ok(sv, B, H, Sk, D) || !strides_ok(so, B, H, Sq, D))
+    RowStrides sq = get_strides(strides, 0, H, Sq, D), sk = get_strides(strides, 1, Hk, Sk, D),
+               sv = get_strides(strides, 2, Hk, Sk, D), so = get_strides(strides, 3, H, Sq, D);
+    if (!strides_ok(sq, B, H, Sq, D) || !strides_ok(sk, B, Hk, Sk, D) || !strides_ok(sv, B, Hk, Sk, D) || !strides_ok(so, B, H, Sq, D))
         return fail(FA_ERR_STRIDE, "strides must be positive multiples of 8 elements with D contiguous");
     DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
     const int BH = B * H;
     CUtensorMap mq, mk, mv, mo;
-    if (!make_map(&mq, q, B, H, Sq, D, sq, dtype, 128) || !make_map(&mk, k, B, H, Sk, D, sk, dtype, 128) ||
-        !make_map(&mv, v, B, H, Sk, D, sv, dtype, 128) || !make_map(&mo, o, B, H, Sq, D, so, dtype, 128))
+    if (!make_map(&mq, q, B, H, Sq, D, sq, dtype, 128) || !make_map(&mk, k, B, Hk, Sk, D, sk, dtype, 128) ||
+        !make_map(&mv, v, B, Hk, Sk, D, sv, dtype, 128) || !make_map(&mo, o, B, H, Sq, D, so, dtype, 128))
         return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (B=%d H=%d Sq=%d Sk=%d D=%d)", B, H, Sq, Sk, D);
     FwdParams p;
-    p.BH = BH; p.H = H; p.Sq = Sq; p.Sk = Sk;
+    p.BH = BH; p.H = H; p.G = H / Hk; p.Sq = Sq; p.Sk = Sk;
     p.n_qblk = (Sq + 255) / 256;
     p.n_items = BH * p.n_qblk;
     p.causal = causal ? 1 : 0;
@@ -222,26 +223,27 @@ int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* 
                        const float* lse, void* dq, void* dk, void* dv, float* delta,
                        int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale, void* stream,
                        int parts) {
-    return fa_sm100_bwd_strided(q, k, v, o, dout, lse, dq, dk, dv, delta, B, H, Sq, Sk, D, dtype, causal, sm_scale,
+    return fa_sm100_bwd_strided(q, k, v, o, dout, lse, dq, dk, dv, delta, B, H, H, Sq, Sk, D, dtype, causal, sm_scale,
                                 nullptr, stream, parts);
 }
 
 int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dout,
                          const float* lse, void* dq, void* dk, void* dv, float* delta,
-                         int B, int H, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                         int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                          const long long* strides, void* stream, int parts) {
     if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta) return fail(FA_ERR_NULL, "null tensor pointer");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
+    if (Hk <= 0 || H % Hk) return fail(FA_ERR_SHAPE, "K/V heads %d must divide query heads %d", Hk, H);
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dout) ||
         !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || !aligned16(lse) || !aligned16(delta))
         return fail(FA_ERR_ALIGN, "all tensors must be 16-byte aligned");
-    RowStrides s_q = get_strides(strides, 0, H, Sq, D), s_k = get_strides(strides, 1, H, Sk, D),
-               s_v = get_strides(strides, 2, H, Sk, D), s_o = get_strides(strides, 3, H, Sq, D),
+    RowStrides s_q = get_strides(strides, 0, H, Sq, D), s_k = get_strides(strides, 1, Hk, Sk, D),
+               s_v = get_strides(strides, 2, Hk, Sk, D), s_o = get_strides(strides, 3, H, Sq, D),
                s_do = get_strides(strides, 4, H, Sq, D), s_dq = get_strides(strides, 5, H, Sq, D),
-               s_dk = get_strides(strides, 6, H, Sk, D), s_dv = get_strides(strides, 7, H, Sk, D);
-    if (!strides_ok(s_q, B, H, Sq, D) || !strides_ok(s_k, B, H, Sk, D) || !strides_ok(s_v, B, H, Sk, D) ||
+               s_dk = get_strides(strides, 6, Hk, Sk, D), s_dv = get_strides(strides, 7, Hk, Sk, D);
+    if (!strides_ok(s_q, B, H, Sq, D) || !strides_ok(s_k, B, Hk, Sk, D) || !strides_ok(s_v, B, Hk, Sk, D) ||
         !strides_ok(s_o, B, H, Sq, D) || !strides_ok(s_do, B, H, Sq, D) || !strides_ok(s_dq, B, H, Sq, D) ||
-        !strides_ok(s_dk, B, H, Sk, D) || !strides_ok(s_dv, B, H, Sk, D))
+        !strides_ok(s_dk, B, Hk, Sk, D) || !strides_ok(s_dv, B, Hk, Sk, D))
         return fail(FA_ERR_STRIDE, "strides must be positive multiples of 8 elements with D contiguous");
     DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -254,13 +256,13 @@ int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void
     }
     if (!(parts & (FA_BWD_DQ | FA_BWD_DKV))) return 0;
     CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
-    if (!make_map(&mq, q, B, H, Sq, D, s_q, dtype, 128) || !make_map(&mk, k, B, H, Sk, D, s_k, dtype, 128) ||
-        !make_map(&mv, v, B, H, Sk, D, s_v, dtype, 128) || !make_map(&mdo, dout, B, H, Sq, D, s_do, dtype, 128) ||
-        !make_map(&mdq, dq, B, H, Sq, D, s_dq, dtype, 128) || !make_map(&mdk, dk, B, H, Sk, D, s_dk, dtype, 128) ||
-        !make_map(&mdv, dv, B, H, Sk, D, s_dv, dtype, 128))
+    if (!make_map(&mq, q, B, H, Sq, D, s_q, dtype, 128) || !make_map(&mk, k, B, Hk, Sk, D, s_k, dtype, 128) ||
+        !make_map(&mv, v, B, Hk, Sk, D, s_v, dtype, 128) || !make_map(&mdo, dout, B, H, Sq, D, s_do, dtype, 128) ||
+        !make_map(&mdq, dq, B, H, Sq, D, s_dq, dtype, 128) || !make_map(&mdk, dk, B, Hk, Sk, D, s_dk, dtype, 128) ||
+        !make_map(&mdv, dv, B, Hk, Sk, D, s_dv, dtype, 128))
         return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (B=%d H=%d Sq=%d Sk=%d D=%d)", B, H, Sq, Sk, D);
     BwdParams p;
-    p.BH = BH; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal ? 1 : 0;
+    p.BH = BH; p.H = H; p.Hk = Hk; p.G = H / Hk; p.Sq = Sq; p.Sk = Sk; p.causal = causal ? 1 : 0;
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;

@@ -29,6 +29,7 @@ namespace fa {
 
 struct BwdParams {
     int BH, H, Sq, Sk, causal;     // 4-D tensor maps [B, H, S, D]: coordinates (col, row, h, b)
+    int Hk, G;                     // K/V heads and query heads per K/V head (GQA/MQA; G = 1: reference layout)
     float scale, scale_log2;
     const float* lse;      // [BH, Sq]
     const float* delta;    // [BH, Sq]
@@ -164,7 +165,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sched_item) + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int n_items = p.BH * p.n_ktiles;
+    const int n_items = (p.BH / p.G) * p.n_ktiles;       // one item per (batch, K/V head, kv tile)
 
     if (tid == 0) {
         mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(s_full1, 1); mbar_init(dp_full, 1);
@@ -185,11 +186,13 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     constexpr bool kDoubleS = (D == 64);
     constexpr uint32_t kColST = 0, kColDPT = kDoubleS ? 256 : 128, kColDV = kDoubleS ? 384 : 256, kColDK = kColDV + D;
 
-    // item -> (bh, kv tile, first q tile, number of q tiles); ascending kv tile = heavy first under causal
+    // item -> (batch*Hk + kv head, kv tile, first q tile, q tiles per query head, iterations); ascending kv tile =
+    // heavy first under causal.  With GQA the item walks the q tiles of every query head of the group, so the
+    // reduction of dK/dV over the group happens in the TMEM accumulators (deterministic, no atomics).
     auto decode = [&](int item, int& bh, int& jt, int& i_start, int& n_it) {
-        bh = item / p.n_ktiles; jt = item % p.n_ktiles;
+        bh = item / p.n_ktiles; jt = item % p.n_ktiles;     // bh = b * Hk + hk
         i_start = p.causal ? jt : 0;                       // first Q tile with a row >= kv_block_start (:341)
-        n_it = max(p.n_qtiles - i_start, 0);
+        n_it = max(p.n_qtiles - i_start, 0) * p.G;
     };
     // consumer side of the scheduler broadcast: a whole warp calls it (lane 0 releases the slot), or one thread alone
     auto next_item = [&](uint32_t ix, bool solo = false) -> int {
@@ -215,35 +218,55 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             const int item = next_item(ix);
             if (item >= n_items) break;
             int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
-            auto fetch = [&](int it, float (&nl)[4], float (&dl)[4]) {
-                const int q0 = (i_start + it) * 128;
-                #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int row = q0 + lane + u * 32;
-                    nl[u] = -INFINITY; dl[u] = 0.f;       // out-of-range query rows: P = exp2(-inf) = 0
-                    if (row < p.Sq) {
-                        const float l = __ldg(p.lse + (size_t)bh * p.Sq + row);
-                        nl[u] = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
-                        dl[u] = __ldg(p.delta + (size_t)bh * p.Sq + row);
+            // (q tile, row offset of the query head) walker over the item's iterations; with GQA it visits every head of the
+            // group.  Lane l owns rows 4l..4l+3 of the tile: one 16-byte load each for LSE and delta (scalar, bounds-checked
+            // loads only for a ragged last tile or an unaligned S_q) and one 16-byte shared store each.
+            int s_qtile = i_start;
+            size_t s_row0 = ((size_t)(bh / p.Hk) * p.H + (size_t)(bh % p.Hk) * p.G) * p.Sq;
+            const bool vec_ok = (p.Sq & 3) == 0;
+            auto fetch = [&](float4& nl, float4& dl) {             // statistics of the walker's current tile, then advance
+                const int q0 = s_qtile * 128 + lane * 4;
+                const size_t off = s_row0 + q0;
+                if (++s_qtile == p.n_qtiles) { s_qtile = i_start; s_row0 += p.Sq; }
+                float l[4];
+                if (vec_ok && q0 + 4 <= p.Sq) {
+                    const float4 lv = __ldg(reinterpret_cast<const float4*>(p.lse + off));
+                    dl = __ldg(reinterpret_cast<const float4*>(p.delta + off));
+                    l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+                } else {
+                    float d[4];
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool in = q0 + u < p.Sq;                 // out-of-range query rows: P = exp2(-inf) = 0
+                        l[u] = in ? __ldg(p.lse + off + u) : INFINITY;
+                        d[u] = in ? __ldg(p.delta + off + u) : 0.f;
                     }
+                    dl = make_float4(d[0], d[1], d[2], d[3]);
                 }
-            };
-            float nl_n[4], dl_n[4];
-            if (n_it > 0) fetch(0, nl_n, dl_n);
-            for (int it = 0; it < n_it; ++it, ++gs) {
-                float nl_c[4], dl_c[4];
                 #pragma unroll
-                for (int u = 0; u < 4; ++u) { nl_c[u] = nl_n[u]; dl_c[u] = dl_n[u]; }
-                if (it + 1 < n_it) fetch(it + 1, nl_n, dl_n);
+                for (int u = 0; u < 4; ++u) l[u] = (l[u] == INFINITY || l[u] == -INFINITY) ? -INFINITY : -l[u] * kLog2e;
+                nl = make_float4(l[0], l[1], l[2], l[3]);
+            };
+            auto publish = [&](const float4& nl, const float4& dl) {
                 const uint32_t ss = gs % C::kStatStages;
                 mbar_wait(&stat_empty[ss], ((gs / C::kStatStages) & 1) ^ 1, 400);
-                #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    sts32(stat_addr + ss * 1024 + (lane + u * 32) * 4, nl_c[u]);
-                    sts32(stat_addr + ss * 1024 + 512 + (lane + u * 32) * 4, dl_c[u]);
-                }
+                sts128(stat_addr + ss * 1024 + lane * 16, __float_as_uint(nl.x), __float_as_uint(nl.y), __float_as_uint(nl.z), __float_as_uint(nl.w));
+                sts128(stat_addr + ss * 1024 + 512 + lane * 16, __float_as_uint(dl.x), __float_as_uint(dl.y), __float_as_uint(dl.z), __float_as_uint(dl.w));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&stat_full[ss]);
+                ++gs;
+            };
+            // two tiles of global loads in flight: with short MMAs (D=64) this warp sits right at the critical path
+            float4 nlA, dlA, nlB, dlB;
+            if (n_it > 0) fetch(nlA, dlA);
+            if (n_it > 1) fetch(nlB, dlB);
+            for (int it = 0; it < n_it; it += 2) {
+                publish(nlA, dlA);
+                if (it + 2 < n_it) fetch(nlA, dlA);
+                if (it + 1 < n_it) {
+                    publish(nlB, dlB);
+                    if (it + 3 < n_it) fetch(nlB, dlB);
+                }
             }
         }
     } else if (warp == 9) {
@@ -265,24 +288,27 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 if (n_it > 0) {
                     mbar_arrive_expect_tx_e(k_full, C::kTileBytes);
                     #pragma unroll
-                    for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sK + c * 16384, &mapK, k_full, c * 64, jt * 128, bh % p.H, bh / p.H);
+                    for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sK + c * 16384, &mapK, k_full, c * 64, jt * 128, bh % p.Hk, bh / p.Hk);
+                    int l_qtile = i_start, hq = (bh % p.Hk) * p.G;     // (q tile, query head) walker of the item
+                    const int bq = bh / p.Hk;
                     for (int it = 0; it < n_it; ++it, ++git) {
                         const uint32_t st = git % C::kStages;
                         uint8_t* sQi = sStage + st * C::kStageBytes;
                         uint8_t* sdOi = sQi + C::kTileBytes;
-                        const int q0 = (i_start + it) * 128;
+                        const int q0 = l_qtile * 128, hcur = hq;
+                        if (++l_qtile == p.n_qtiles) { l_qtile = i_start; ++hq; }
                         mbar_wait(&stage_empty[st], ((git / C::kStages) & 1) ^ 1, 410);
                         mbar_arrive_expect_tx_e(&q_full[st], C::kTileBytes);
                         #pragma unroll
-                        for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sQi + c * 16384, &mapQ, &q_full[st], c * 64, q0, bh % p.H, bh / p.H);
+                        for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sQi + c * 16384, &mapQ, &q_full[st], c * 64, q0, hcur, bq);
                         if (it == 0) {
                             mbar_arrive_expect_tx_e(v_full, C::kTileBytes);
                             #pragma unroll
-                            for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sV + c * 16384, &mapV, v_full, c * 64, jt * 128, bh % p.H, bh / p.H);
+                            for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sV + c * 16384, &mapV, v_full, c * 64, jt * 128, bh % p.Hk, bh / p.Hk);
                         }
                         mbar_arrive_expect_tx_e(&do_full[st], C::kTileBytes);
                         #pragma unroll
-                        for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sdOi + c * 16384, &mapdO, &do_full[st], c * 64, q0, bh % p.H, bh / p.H);
+                        for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sdOi + c * 16384, &mapdO, &do_full[st], c * 64, q0, hcur, bq);
                     }
                     ++nacc;
                 }
@@ -365,11 +391,13 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             if (item >= n_items) break;
             int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
             const int kv_g = jt * 128 + r;
+            int qtile = i_start;                          // q tile of the current iteration (wraps per query head of the group)
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it;
                 const uint32_t ss = g % C::kStatStages;
                 const uint32_t stat = smem_u32(sStat) + ss * 1024 + h * 256;
-                const int q0 = (i_start + it) * 128 + h * 64;       // global query index of my column 0
+                const int q0 = qtile * 128 + h * 64;                 // global query index of my column 0
+                if (++qtile == p.n_qtiles) qtile = i_start;
                 mbar_wait(&stat_full[ss], (g / C::kStatStages) & 1, 430);
                 const uint32_t tSTi = tST + (kDoubleS ? (g & 1) * 128 : 0);
                 if (kDoubleS) mbar_wait((g & 1) ? s_full1 : s_full, (g >> 1) & 1, 431);
@@ -450,8 +478,8 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             if (tid == 0) {
                 #pragma unroll
                 for (int c = 0; c < C::kChunks; ++c) {
-                    tma_store_4d(&mapdV, sOutV + c * 16384, c * 64, jt * 128, bh % p.H, bh / p.H);
-                    tma_store_4d(&mapdK, sOutK + c * 16384, c * 64, jt * 128, bh % p.H, bh / p.H);
+                    tma_store_4d(&mapdV, sOutV + c * 16384, c * 64, jt * 128, bh % p.Hk, bh / p.Hk);
+                    tma_store_4d(&mapdK, sOutK + c * 16384, c * 64, jt * 128, bh % p.Hk, bh / p.Hk);
                 }
                 tma_store_commit();
                 if (!C::kSepStage) { tma_store_wait_read0(); mbar_arrive(kv_free); }   // staging aliases K/V
@@ -572,7 +600,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 mbar_wait(&k_empty[ks], ((g / C::kKStages) & 1) ^ 1, 510);
                 mbar_arrive_expect_tx_e(&k_full[ks], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, bh % p.H, bh / p.H);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, (bh % p.H) / p.G, bh / p.H);
                 if (it == 0) {
                     mbar_arrive_expect_tx_e(do_full, C::kTileBytes);
                     #pragma unroll
@@ -581,7 +609,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 mbar_wait(&v_empty[vs], ((g / C::kVStages) & 1) ^ 1, 511);
                 mbar_arrive_expect_tx_e(&v_full[vs], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, bh % p.H, bh / p.H);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, (bh % p.H) / p.G, bh / p.H);
             }
             if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dq, 1u) + (int)gridDim.x : n_items;
             item = __shfl_sync(0xffffffffu, item, 0);
@@ -750,7 +778,7 @@ int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
         if (e != cudaSuccess) return (int)e;
     }
     if (parts & 4) {
-        const int items = p.BH * p.n_ktiles;
+        const int items = (p.BH / p.G) * p.n_ktiles;
         const int grid = FA_BWD_PERSISTENT ? (items < p.sms ? items : p.sms) : items;
         fa_bwd_dkv_kernel<D, kBf16><<<grid, kBwdThreads, DkvCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
     }

@@ -22,6 +22,7 @@ namespace fa {
 
 struct FwdParams {
     int BH, H, Sq, Sk;     // tensor maps are 4-D [B, H, S, D] with explicit strides: coordinates (col, row, h, b)
+    int G;                 // query heads per K/V head (GQA/MQA; 1 = the reference's layout): kv head = h / G
     int n_qblk;            // ceil(Sq / 256)
     int n_items;           // BH * n_qblk
     int causal;
@@ -161,7 +162,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     mbar_arrive_expect_tx_e(&kv_full[st], C::kTileBytes);
                     #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c)
-                        tma_load_4d_e(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, j * 128, bh % p.H, bh / p.H);
+                        tma_load_4d_e(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, j * 128, (bh % p.H) / p.G, bh / p.H);
                     ++kv_cnt;
                 };
                 if (n0 > 0) load_q(0, q_cnt0);

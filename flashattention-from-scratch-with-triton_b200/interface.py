@@ -65,7 +65,7 @@ def flash_attention_forward(Q, K, V, is_causal, sm_scale=None):
     st = _strides(Q, K, V, O)
     with torch.cuda.device(Q.device):
         rc = lib.fa_sm100_fwd_strided(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), LSE.data_ptr(),
-                                      B, H, S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                      B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
                                       float(sm_scale) if sm_scale is not None else 0.0, st, _stream(Q))
     _cabi.check("fa_sm100_fwd_strided", rc)
     return O, LSE
@@ -83,7 +83,7 @@ def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_ca
     with torch.cuda.device(Q.device):
         rc = lib.fa_sm100_bwd_strided(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
                                       LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
-                                      B, H, S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                      B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
                                       float(sm_scale) if sm_scale is not None else 0.0, st, _stream(Q), int(parts))
     _cabi.check("fa_sm100_bwd_strided", rc)
 
@@ -112,6 +112,7 @@ class FlashAttentionFunction(torch.autograd.Function):
         assert Q.shape[-1] == K.shape[-1] == V.shape[-1]                   # :135
         assert Q.ndim == 4 and K.ndim == 4 and V.ndim == 4                 # :136
         assert K.dtype == Q.dtype and V.dtype == Q.dtype
+        assert K.shape[:3] == V.shape[:3] and K.shape[0] == Q.shape[0] and Q.shape[1] % K.shape[1] == 0   # GQA/MQA: Hk | H
         Q_ = as_kernel_layout(Q); K_ = as_kernel_layout(K); V_ = as_kernel_layout(V)   # :138-140, without needless copies
         O, LSE = flash_attention_forward(Q_, K_, V_, is_causal, sm_scale)
         ctx.save_for_backward(Q_, K_, V_, O, LSE)                          # :145 (same set, same order)

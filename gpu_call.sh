@@ -1,5 +1,2 @@
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/c32_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/c32_pytest.log
-timeout 200 python scripts/ab_time.py all 2>/dev/null | cut -c1-400
-timeout 300 python bench.py --steps 20 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('bench', round(d['value'],1), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), {k:round(v['ms'],4) for k,v in d['kernels'].items()})"
+for v in pregqa st5 pregqa st5; do FA_SM100_LIB=$PWD/build/variants/libfa_sm100_$v.so timeout 200 python scripts/ab_dkv.py 2>&1 | tail -1 | cut -c1-200; done
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "gqa or oracle or bshd or out_of_bounds or golden" 2>&1 | tail -2

@@ -59,13 +59,15 @@ int fa_sm100_bwd(const void* q, const void* k, const void* v, const void* o, con
  * (16 bytes) and the base is 16-byte aligned — e.g. [B,H,S,D] views of a [B,S,H,D] buffer coming straight out of
  * a QKV projection, without the .contiguous() copy the reference makes (code/My_FlashAttention_optimized.py:138-140).
  * `strides` holds 3 element strides {batch, head, row} per tensor, in the order q,k,v,o (fwd) and
- * q,k,v,o,dout,dq,dk,dv (bwd); NULL means all contiguous.  lse and delta stay contiguous [B,H,Sq] fp32. */
+ * q,k,v,o,dout,dq,dk,dv (bwd); NULL means all contiguous.  lse and delta stay contiguous [B,H,Sq] fp32.
+ * Hk = number of K/V heads (GQA / MQA): k, v, dk, dv are [B,Hk,Sk,D] and query head h uses K/V head h / (H/Hk);
+ * Hk must divide H, Hk = H is the reference's layout.  dk/dv are reduced over the group inside the kernel. */
 int fa_sm100_fwd_strided(const void* q, const void* k, const void* v, void* o, float* lse,
-                         int B, int H, int Sq, int Sk, int D, int dtype, int causal,
+                         int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal,
                          float sm_scale, const long long* strides, void* stream);
 int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dout,
                          const float* lse, void* dq, void* dk, void* dv, float* delta,
-                         int B, int H, int Sq, int Sk, int D, int dtype, int causal,
+                         int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal,
                          float sm_scale, const long long* strides, void* stream, int parts);
 #define FA_ERR_STRIDE (-8)    /* a stride is not a multiple of 8 elements or is negative */
 

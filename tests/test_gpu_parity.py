@@ -302,3 +302,31 @@ def test_bshd_strided_inputs_zero_copy(D, causal):
     assert not fa.tma_compatible(odd)
     assert _close(fa.flash_attention(odd, odd, odd, causal).cpu(),
                   orc.closed_form(odd.cpu(), odd.cpu(), odd.cpu(), None, causal)[0])
+
+
+@pytest.mark.parametrize("causal", [False, True], ids=["full", "causal"])
+@pytest.mark.parametrize("H,Hk,D", [(8, 2, 64), (4, 1, 128), (6, 3, 128)], ids=["gqa4", "mqa", "gqa2"])
+def test_gqa_mqa_head_sharing(H, Hk, D, causal):
+    """K/V with Hk heads shared by groups of H/Hk query heads: equals attention with K/V repeated per query head,
+    and dK/dV equal the group sums (reduced inside the dK/dV kernel, deterministic)."""
+    B, Sq, Sk = 2, 320, 448 if not causal else 320
+    g = torch.Generator().manual_seed(21)
+    Q = torch.randn(B, H, Sq, D, generator=g).bfloat16(); dO = torch.randn(B, H, Sq, D, generator=g).bfloat16()
+    K = torch.randn(B, Hk, Sk, D, generator=g).bfloat16(); V = torch.randn(B, Hk, Sk, D, generator=g).bfloat16()
+    q, k, v = (t.cuda().requires_grad_(True) for t in (Q, K, V))
+    O = fa.flash_attention(q, k, v, causal); O.backward(dO.cuda())
+    assert k.grad.shape == K.shape and v.grad.shape == V.shape
+    G = H // Hk
+    Ke, Ve = K.repeat_interleave(G, dim=1), V.repeat_interleave(G, dim=1)
+    rO, _, rdQ, rdKe, rdVe = orc.closed_form(Q, Ke, Ve, dO, causal)
+    rdK = rdKe.reshape(B, Hk, G, Sk, D).sum(2); rdV = rdVe.reshape(B, Hk, G, Sk, D).sum(2)
+    for name, x, r in (("O", O, rO), ("dQ", q.grad, rdQ), ("dK", k.grad, rdK), ("dV", v.grad, rdV)):
+        tol = 1e-2 if name in ("O", "dQ") else 2e-2          # dK/dV: G-fold sums of bf16-rounded products
+        assert _close(x.detach().cpu(), r, tol, tol), (name, (x.detach().cpu().float() - r.float()).abs().max())
+    # bitwise the same as running the expanded problem's forward through the non-GQA path
+    Oe = fa.flash_attention(Q.cuda(), Ke.cuda(), Ve.cuda(), causal)
+    assert torch.equal(O.detach(), Oe)
+    k2, v2 = (t.cuda().requires_grad_(True) for t in (K, V))
+    q2 = Q.cuda().requires_grad_(True)
+    fa.flash_attention(q2, k2, v2, causal).backward(dO.cuda())
+    assert torch.equal(k2.grad, k.grad) and torch.equal(v2.grad, v.grad)      # deterministic
