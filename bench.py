@@ -13,8 +13,8 @@ no data-path collective => "scaling": "weak"; `value` is the aggre
 time is the max over ranks.
 
 One JSON line on stdout (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (dK/dV backward) against the MEASURED dense-bf16 peak
-  kernels       per-kernel ms / algorithmic TFLOP/s / fraction (fwd, delta, dQ, dKV), timed individually
+  roofline      dominant kernel (the backward kernel) against the MEASURED dense-bf16 peak
+  kernels       per-kernel ms / algorithmic TFLOP/s / fraction (fwd, delta, fused + convert at D=64 | dQ, dKV), timed individually
   cpu_baseline  the CPU ground-truth path (PyTorch SDPA on the host cores) on the same workload
   e2e           same metric with pinned-host inputs and outputs, H2D/D2H copies inside the timed region
   also          kernel-level numbers of the D=128 configs (C3 and one 8-GPU shard of C4), untimed extras
@@ -150,7 +150,9 @@ def make_inputs(B, H, S, D, dtype, seed, device):
 
 def kernel_breakdown(fa, Q, K, V, dO, causal, steps, warmup, flush, peak):
     """Per-kernel CUDA-event timing through the C ABI.  Algorithmic FLOPs per launch = GEMM count of the
-    kernel's algorithm (fwd 2, dQ 3, dKV 4) x 2*B*H*Sq*Sk*D/(2 if causal)."""
+    kernel's algorithm (fwd 2, dQ 3, dKV 4, fused dK/dV/dQ 5) x 2*B*H*Sq*Sk*D/(2 if causal).
+    Head dim 64 runs the fused backward (delta+zeroing, fused, conversion); the two-kernel backward of the
+    deterministic mode is timed beside it."""
     import torch
     B, H, S, D = Q.shape
     O, LSE = fa.flash_attention_forward(Q, K, V, causal)
@@ -159,12 +161,18 @@ def kernel_breakdown(fa, Q, K, V, dO, causal, steps, warmup, flush, peak):
     fa.flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, causal, 7)
     gemm = 2.0 * B * H * S * S * D / (2 if causal else 1)
     T = Q.numel() * Q.element_size()
-    parts = {
-        "fwd": (lambda: fa.flash_attention_forward(Q, K, V, causal), 2 * gemm, "tensor"),
-        "delta": (lambda: fa.flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, causal, 1), None, "hbm"),
-        "dQ": (lambda: fa.flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, causal, 2), 3 * gemm, "tensor"),
-        "dKV": (lambda: fa.flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, causal, 4), 4 * gemm, "tensor"),
-    }
+    two = lambda part: (lambda: fa.flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, causal, part))
+    dbytes = 2 * T + B * H * S * 4                       # read O, dO; write delta
+    parts = {"fwd": (lambda: fa.flash_attention_forward(Q, K, V, causal), 2 * gemm, "tensor")}
+    if D == 64 and not fa.is_deterministic():
+        acc = torch.empty(B, H, S, D, dtype=torch.float32, device=Q.device)
+        fus = lambda part: (lambda: fa.flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, causal, dq_acc=acc, parts=part))
+        parts.update({"delta": (fus(1), dbytes + 2 * T, "hbm"),         # + zeros into the fp32 dQ workspace
+                      "fused": (fus(8), 5 * gemm, "tensor"),
+                      "convert": (fus(16), 3 * T, "hbm"),               # read fp32 workspace, write 16-bit dQ
+                      "two_kernel_dQ": (two(2), 3 * gemm, "tensor"), "two_kernel_dKV": (two(4), 4 * gemm, "tensor")})
+    else:
+        parts.update({"delta": (two(1), dbytes, "hbm"), "dQ": (two(2), 3 * gemm, "tensor"), "dKV": (two(4), 4 * gemm, "tensor")})
     out = {}
     for name, (fn, flops, bound) in parts.items():
         ts = time_steps(fn, steps, warmup, flush)
@@ -173,8 +181,7 @@ def kernel_breakdown(fa, Q, K, V, dO, causal, steps, warmup, flush, peak):
             ach = flops / (ms * 1e-3) / 1e12
             out[name] = dict(ms=ms, bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peak["bf16_burst"])
         else:
-            byts = 2 * T + B * H * S * 4                 # read O, dO; write delta
-            ach = byts / (ms * 1e-3) / 1e9
+            ach = flops / (ms * 1e-3) / 1e9              # bytes
             out[name] = dict(ms=ms, bound="hbm", achieved=ach, unit="GB/s", frac=ach / peak["hbm"])
     return out
 
@@ -344,14 +351,15 @@ def main():
     if rank == 0 and not a.no_extras:
         if a.impl == "ours":
             kb = kernel_breakdown(fa, Q.detach(), K.detach(), V.detach(), dO, causal, max(5, a.steps // 2), 3, flush, peak)
-            dom = max((k for k in kb if kb[k]["bound"] == "tensor"), key=lambda k: kb[k]["ms"])
+            dom = max((k for k in kb if kb[k]["bound"] == "tensor" and not k.startswith("two_kernel")), key=lambda k: kb[k]["ms"])
             gemm = 2.0 * B * H * S * S * D / (2 if causal else 1)
             line["kernels"] = kb
-            line["roofline"] = {"kernel": {"fwd": "fa_fwd_kernel", "dQ": "fa_bwd_dq_kernel", "dKV": "fa_bwd_dkv_kernel"}[dom],
+            line["roofline"] = {"kernel": {"fwd": "fa_fwd_kernel", "dQ": "fa_bwd_dq_kernel", "dKV": "fa_bwd_dkv_kernel",
+                                           "fused": "fa_bwd_fused_kernel"}[dom],
                                 "bound": "tensor", "achieved": kb[dom]["achieved"], "peak": peak["bf16_burst"],
                                 "unit": "TFLOP/s", "frac": kb[dom]["frac"], "traffic": ncu_traffic(a.workload, dom),
                                 "peak_kind": "burst, " + peak["source"],
-                                "algorithmic_flops_per_launch": {"fwd": 2, "dQ": 3, "dKV": 4}[dom] * gemm}
+                                "algorithmic_flops_per_launch": {"fwd": 2, "dQ": 3, "dKV": 4, "fused": 5}[dom] * gemm}
             also = {}
             for wl in ("C3", "C4s"):
                 if wl == a.workload:
@@ -360,7 +368,7 @@ def main():
                 q2, k2, v2, do2 = make_inputs(b2, h2, s2, d2, dtype, 7, dev)
                 kb2 = kernel_breakdown(fa, q2, k2, v2, do2, c2, 5, 3, flush, peak)
                 f2 = 4.0 * b2 * h2 * s2 * s2 * d2 / (2 if c2 else 1)
-                t_all = sum(kb2[k]["ms"] for k in kb2)
+                t_all = sum(kb2[k]["ms"] for k in kb2 if not k.startswith("two_kernel"))
                 also[wl] = dict(fwd_tflops=f2 / (kb2["fwd"]["ms"] * 1e-3) / 1e12,
                                 fwd_frac_of_measured_peak=f2 / (kb2["fwd"]["ms"] * 1e-3) / 1e12 / peak["bf16_burst"],
                                 fwd_bwd_tflops=3.5 * f2 / (t_all * 1e-3) / 1e12,

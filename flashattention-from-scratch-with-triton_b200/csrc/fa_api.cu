@@ -3,6 +3,7 @@
 // pre-hooks, code/My_FlashAttention_optimized.py:33-51 and kernel file :7-16), launches.
 #include "fa_fwd.cuh"
 #include "fa_bwd.cuh"
+#include "fa_bwd_fused.cuh"
 #include "fa_aux.cuh"
 #include "../../include/fa_sm100.h"
 
@@ -58,6 +59,21 @@ bool make_map(CUtensorMap* m, const void* ptr, int B, int H, int S, int D, const
     return r == CUDA_SUCCESS;
 }
 
+// fp32 accumulator [BH, S, D] (contiguous) as a 3-D map, box = [1][128 rows][32 columns = 128 B], SWIZZLE_128B: target of the
+// fused backward's cp.reduce.async.bulk.tensor (.add); rows past S are dropped
+bool make_map_acc(CUtensorMap* m, const float* ptr, int BH, int S, int D) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)BH};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)S * D * 4};
+    cuuint32_t box[3] = {32, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // strides of tensor `i` from the caller's array (NULL = contiguous [B,H,S,D]); size-1 dims get a harmless stride
 RowStrides get_strides(const long long* strides, int i, int H, int S, int D) {
     RowStrides st{(long long)H * S * D, (long long)S * D, (long long)D};
@@ -108,6 +124,15 @@ int check_common(int B, int H, int Sq, int Sk, int D, int dtype) {
     if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return fail(FA_ERR_SHAPE, "non-positive dimension B=%d H=%d Sq=%d Sk=%d", B, H, Sq, Sk);
     if ((long long)B * H > 2147483647LL / 4) return fail(FA_ERR_SHAPE, "B*H too large");
     return 0;
+}
+// heads per scheduling chunk: as many heads as keep their tensors (bytes_per_head each) inside ~48 MB of the 126 MB L2,
+// balanced over the chunks
+int heads_per_chunk(int n_heads, double bytes_per_head) {
+    long long hc = (long long)(48.0 * 1024 * 1024 / bytes_per_head);
+    if (hc < 1) hc = 1;
+    if (hc > n_heads) hc = n_heads;
+    const int n_chunks = (int)((n_heads + hc - 1) / hc);
+    return (n_heads + n_chunks - 1) / n_chunks;
 }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -176,6 +201,7 @@ int fa_sm100_fwd_strided(const void* q, const void* k, const void* v, void* o, f
     p.BH = BH; p.H = H; p.G = H / Hk; p.Sq = Sq; p.Sk = Sk;
     p.n_qblk = (Sq + 255) / 256;
     p.n_items = BH * p.n_qblk;
+    p.hc = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
     p.causal = causal ? 1 : 0;
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
@@ -268,6 +294,8 @@ int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void
     p.lse = lse; p.delta = delta;
     p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
     p.sms = dev->sms;
+    p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
+    p.hc_dkv = heads_per_chunk(BH / p.G, 4.0 * ((double)p.G * Sq + Sk) * D);
     {   // two scheduler counters from the ring, zeroed on the stream ahead of the kernels
         const unsigned int slot = g_sched_next.fetch_add(2) % (kSchedRing - 1);
         p.sched_dkv = dev->sched_ring + slot; p.sched_dq = dev->sched_ring + slot + 1;
@@ -277,6 +305,65 @@ int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void
     rc = launch_bwd(mq, mk, mv, mdo, mdq, mdk, mdv, p, D, dtype, parts, st);
     g_launches += ((parts & FA_BWD_DQ) ? 1 : 0) + ((parts & FA_BWD_DKV) ? 1 : 0);
     return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_bwd kernels launch");
+}
+
+size_t fa_sm100_bwd_fused_workspace(int B, int H, int Sq, int D) {
+    if (D != 64 || B <= 0 || H <= 0 || Sq <= 0) return 0;
+    return (size_t)B * H * Sq * D * sizeof(float);
+}
+
+int fa_sm100_bwd_fused(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                       const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_acc,
+                       int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                       const long long* strides, void* stream, int parts) {
+    if (parts == 0) parts = FA_BWD_DELTA | FA_BWD_FUSED | FA_BWD_CONVERT;
+    if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta || !dq_acc) return fail(FA_ERR_NULL, "null tensor pointer");
+    if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
+    if (D != 64) return fail(FA_ERR_HEADDIM, "the fused backward exists for head dim 64 only (TMEM budget), got %d", D);
+    if (Hk <= 0 || H % Hk) return fail(FA_ERR_SHAPE, "K/V heads %d must divide query heads %d", Hk, H);
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dout) || !aligned16(dq) ||
+        !aligned16(dk) || !aligned16(dv) || !aligned16(lse) || !aligned16(delta) || !aligned16(dq_acc))
+        return fail(FA_ERR_ALIGN, "all tensors must be 16-byte aligned");
+    RowStrides s_q = get_strides(strides, 0, H, Sq, D), s_k = get_strides(strides, 1, Hk, Sk, D),
+               s_v = get_strides(strides, 2, Hk, Sk, D), s_o = get_strides(strides, 3, H, Sq, D),
+               s_do = get_strides(strides, 4, H, Sq, D), s_dq = get_strides(strides, 5, H, Sq, D),
+               s_dk = get_strides(strides, 6, Hk, Sk, D), s_dv = get_strides(strides, 7, Hk, Sk, D);
+    if (!strides_ok(s_q, B, H, Sq, D) || !strides_ok(s_k, B, Hk, Sk, D) || !strides_ok(s_v, B, Hk, Sk, D) ||
+        !strides_ok(s_o, B, H, Sq, D) || !strides_ok(s_do, B, H, Sq, D) || !strides_ok(s_dq, B, H, Sq, D) ||
+        !strides_ok(s_dk, B, Hk, Sk, D) || !strides_ok(s_dv, B, Hk, Sk, D))
+        return fail(FA_ERR_STRIDE, "strides must be positive multiples of 8 elements with D contiguous");
+    DeviceInfo* dev; if (int rc = device_info(&dev)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int BH = B * H;
+    CUtensorMap mq, mk, mv, mdo, mdk, mdv, macc;
+    if (!make_map(&mq, q, B, H, Sq, D, s_q, dtype, 128) || !make_map(&mk, k, B, Hk, Sk, D, s_k, dtype, 128) ||
+        !make_map(&mv, v, B, Hk, Sk, D, s_v, dtype, 128) || !make_map(&mdo, dout, B, H, Sq, D, s_do, dtype, 128) ||
+        !make_map(&mdk, dk, B, Hk, Sk, D, s_dk, dtype, 128) || !make_map(&mdv, dv, B, Hk, Sk, D, s_dv, dtype, 128) ||
+        !make_map_acc(&macc, dq_acc, BH, Sq, D))
+        return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (B=%d H=%d Sq=%d Sk=%d D=%d)", B, H, Sq, Sk, D);
+    // delta = rowsum(dO o O) and, in the same pass, zeros into the dQ accumulator
+    int rc = 0;
+    if (parts & FA_BWD_DELTA) {
+        rc = launch_delta(o, dout, delta, (long long)BH * Sq, H, Sq, s_o, s_do, D, dtype, dev->sms, st, dq_acc);
+        ++g_launches;
+        if (rc) return cuda_fail((cudaError_t)rc, "fa_delta_kernel launch");
+    }
+    BwdParams p;
+    p.BH = BH; p.H = H; p.Hk = Hk; p.G = H / Hk; p.Sq = Sq; p.Sk = Sk; p.causal = causal ? 1 : 0;
+    p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
+    p.scale_log2 = p.scale * 1.44269504088896340736f;
+    p.lse = lse; p.delta = delta;
+    p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
+    p.sms = dev->sms;
+    p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
+    p.hc_dkv = heads_per_chunk(BH / p.G, 4.0 * ((double)p.G * Sq + Sk) * D);
+    p.sched_dkv = dev->sched_ring + (g_sched_next.fetch_add(1) % kSchedRing); p.sched_dq = nullptr;
+    cudaError_t e = cudaMemsetAsync(p.sched_dkv, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(sched)");
+    rc = dtype ? launch_bwd_fused_t<true>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts)
+               : launch_bwd_fused_t<false>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts);
+    g_launches += ((parts & FA_BWD_FUSED) ? 1 : 0) + ((parts & FA_BWD_CONVERT) ? 1 : 0);
+    return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_bwd_fused kernels launch");
 }
 
 }  // extern "C"

@@ -34,7 +34,7 @@ struct RowStrides { long long b, h, r; };
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(256) fa_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ dout,
                                                        float* __restrict__ delta, long long rows, int H, int Sq,
-                                                       RowStrides so, RowStrides sd) {
+                                                       RowStrides so, RowStrides sd, float4* __restrict__ zero_acc) {
     constexpr int TPR = D / 8;                       // threads per row
     constexpr int RPB = 256 / TPR;                   // rows per block per step
     const int sub = threadIdx.x % TPR;
@@ -50,20 +50,24 @@ __global__ void __launch_bounds__(256) fa_delta_kernel(const uint4* __restrict__
         #pragma unroll
         for (int off = TPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(row_group_mask<TPR>(), acc, off);
         if (sub == 0) delta[row] = acc;
+        if (zero_acc) {                              // fused backward: clear the fp32 dQ accumulator [rows, D] on the way
+            zero_acc[row * (D / 4) + sub * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            zero_acc[row * (D / 4) + sub * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
 inline int launch_delta(const void* o, const void* dout, float* delta, long long rows, int H, int Sq, RowStrides so,
-                        RowStrides sd, int D, int dtype, int sms, cudaStream_t st) {
+                        RowStrides sd, int D, int dtype, int sms, cudaStream_t st, float* zero_acc = nullptr) {
     const int rpb = 256 / (D / 8);
     long long blocks = (rows + rpb - 1) / rpb;
     const long long cap = (long long)sms * 16;
     if (blocks > cap) blocks = cap;
     const uint4* o4 = (const uint4*)o; const uint4* d4 = (const uint4*)dout;
-    if (D == 64) { if (dtype) fa_delta_kernel<64, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd);
-                   else fa_delta_kernel<64, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd); }
-    else         { if (dtype) fa_delta_kernel<128, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd);
-                   else fa_delta_kernel<128, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd); }
+    if (D == 64) { if (dtype) fa_delta_kernel<64, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc);
+                   else fa_delta_kernel<64, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc); }
+    else         { if (dtype) fa_delta_kernel<128, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc);
+                   else fa_delta_kernel<128, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc); }
     return (int)cudaGetLastError();
 }
 

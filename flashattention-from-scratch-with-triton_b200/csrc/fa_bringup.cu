@@ -40,6 +40,21 @@ static CUtensorMap make_map_2d(void* ptr, uint64_t rows, uint64_t cols, uint32_t
     return m;
 }
 
+// 2-D row-major [rows][cols] fp32 tensor, box = [box_rows][32 cols] (128 B), SWIZZLE_128B: the dQ accumulator of the
+// fused backward, target of cp.reduce.async.bulk.tensor (.add)
+static CUtensorMap make_map_2d_f32(void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    static EncodeTiledFn enc = get_encode();
+    CUtensorMap m;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled(f32) failed %d\n", (int)r); exit(2); }
+    return m;
+}
+
 struct GemmParams {
     int a_chunks, b_chunks;         // number of [rows x 64] boxes loaded for A and B
     int a_rows, b_rows;             // rows per box
@@ -52,13 +67,15 @@ struct GemmParams {
     int a_from_tmem;                // 1: A is written to TMEM by the threads (packed 16-bit pairs)
     int a_tmem_kstep_cols;          // TMEM column advance per k-step for A
     int bf16;
-    int store_mode;                 // 0: D fp32 to global via registers; 1: also TMA-store a 16-bit copy
+    int store_mode;                 // 0: D fp32 to global via registers; 1: also TMA-store a 16-bit copy;
+                                    // 2: also reduce-add the fp32 tile twice into R_out through mapRed (TMA .add)
 };
 
 // D[128 x n] = A[128 x K] * B   (B either [n x K] K-major or [K x n] MN-major, per descriptors)
 __global__ void __launch_bounds__(128, 1)
 bringup_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-             const __grid_constant__ CUtensorMap mapOut, const uint16_t* __restrict__ A_gmem, int a_ld,
+             const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRed,
+             const uint16_t* __restrict__ A_gmem, int a_ld,
              float* __restrict__ D_out, GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,6 +146,12 @@ bringup_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         tc_wait_ld();
         #pragma unroll
         for (int j = 0; j < 32; ++j) D_out[(size_t)tid * p.n + c0 + j] = __uint_as_float(v[j]);
+        if (p.store_mode == 2) {
+            // fp32 staging, one [128 rows][32 floats] SWIZZLE_128B box per 32 columns
+            #pragma unroll
+            for (int g = 0; g < 8; ++g)
+                sts128(smem_u32(sO) + (c0 / 32) * 16384 + sw128_offset(tid, g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
         if (p.store_mode == 1) {
             // stage a 16-bit copy in SWIZZLE_128B layout for the TMA store test
             int chunk = c0 / 64;
@@ -154,6 +177,17 @@ bringup_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             tma_store_wait_all0();
         }
     }
+    if (p.store_mode == 2) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            for (int rep = 0; rep < 2; ++rep) {
+                for (int c = 0; c < p.n / 32; ++c) tma_reduce_add_2d(&mapRed, sO + c * 16384, c * 32, 0);
+                tma_store_commit();
+            }
+            tma_store_wait_all0();
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -172,6 +206,7 @@ struct TestCfg {
     const char* name; bool expected;
     int K, N; bool b_mn_major; bool a_from_tmem; bool bf16; int store_mode;
     uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep; int a_tmem_kstep_cols;
+    bool a_mn_major = false;        // A stored [K rows][128 M columns] (M contiguous): the fused backward's dS^T buffer
 };
 
 static bool run_test(const TestCfg& t) {
@@ -185,45 +220,55 @@ static bool run_test(const TestCfg& t) {
     std::vector<float> ref((size_t)M * N, 0.f);
     for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
         float acc = 0.f;
-        for (int k = 0; k < K; ++k) acc += fA[(size_t)m * K + k] * (t.b_mn_major ? fB[(size_t)k * N + n] : fB[(size_t)n * K + k]);
+        for (int k = 0; k < K; ++k) acc += (t.a_mn_major ? fA[(size_t)k * M + m] : fA[(size_t)m * K + k]) * (t.b_mn_major ? fB[(size_t)k * N + n] : fB[(size_t)n * K + k]);
         ref[(size_t)m * N + n] = acc;
     }
-    uint16_t *dA, *dB, *dO16; float* dD;
+    uint16_t *dA, *dB, *dO16; float *dD, *dR;
     CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2));
     CK(cudaMalloc(&dD, (size_t)M * N * 4)); CK(cudaMalloc(&dO16, (size_t)M * N * 2));
     CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemset(dD, 0xff, (size_t)M * N * 4)); CK(cudaMemset(dO16, 0xff, (size_t)M * N * 2));
+    CK(cudaMalloc(&dR, (size_t)M * N * 4));
+    { std::vector<float> ones((size_t)M * N, 1.0f); CK(cudaMemcpy(dR, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice)); }
 
     GemmParams p; memset(&p, 0, sizeof(p));
     p.a_chunks = K / 64; p.a_rows = 128; p.a_chunk_bytes = 128 * 128; p.a_chunk_ksteps = 4;
+    if (t.a_mn_major) { p.a_chunks = M / 64; p.a_rows = K; p.a_chunk_bytes = K * 128; p.a_chunk_ksteps = 1 << 20; }
     p.a_lbo = t.a_lbo; p.a_sbo = t.a_sbo; p.a_kstep = t.a_kstep;
     if (t.b_mn_major) { p.b_chunks = N / 64; p.b_rows = K; p.b_chunk_bytes = K * 128; p.b_chunk_ksteps = 1 << 20; }
     else              { p.b_chunks = K / 64; p.b_rows = N; p.b_chunk_bytes = N * 128; p.b_chunk_ksteps = 4; }
     p.b_lbo = t.b_lbo; p.b_sbo = t.b_sbo; p.b_kstep = t.b_kstep;
-    p.idesc = make_idesc(t.bf16, false, t.b_mn_major, 128, N);
+    p.idesc = make_idesc(t.bf16, t.a_mn_major, t.b_mn_major, 128, N);
     p.nk = K / 16; p.n = N; p.a_from_tmem = t.a_from_tmem; p.a_tmem_kstep_cols = t.a_tmem_kstep_cols;
     p.bf16 = t.bf16; p.store_mode = t.store_mode;
 
-    CUtensorMap mA = make_map_2d(dA, M, K, 128, t.bf16);
+    CUtensorMap mA = t.a_mn_major ? make_map_2d(dA, K, M, K, t.bf16) : make_map_2d(dA, M, K, 128, t.bf16);
+    CUtensorMap mR = make_map_2d_f32(dR, M, N, 128);
     CUtensorMap mB = t.b_mn_major ? make_map_2d(dB, K, N, K, t.bf16) : make_map_2d(dB, N, K, N, t.bf16);
     CUtensorMap mO = make_map_2d(dO16, M, N, 128, t.bf16);
-    const int smem_bytes = 98304 + 1024;
+    const int smem_bytes = 131072 + 1024;
     CK(cudaFuncSetAttribute(bringup_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    bringup_gemm<<<1, 128, smem_bytes>>>(mA, mB, mO, dA, K, dD, p);
+    bringup_gemm<<<1, 128, smem_bytes>>>(mA, mB, mO, mR, dA, K, dD, p);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         printf("FAIL %-40s launch error: %s\n", t.name, cudaGetErrorString(e));
         return false;   // context is likely dead after a trap; caller exits
     }
-    std::vector<float> hD((size_t)M * N); std::vector<uint16_t> hO((size_t)M * N);
+    std::vector<float> hD((size_t)M * N), hR((size_t)M * N); std::vector<uint16_t> hO((size_t)M * N);
     CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hR.data(), dR, hR.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hO.data(), dO16, hO.size() * 2, cudaMemcpyDeviceToHost));
     double maxerr = 0, maxerr16 = 0; int bad = 0, first_bad = -1;
     for (size_t i = 0; i < hD.size(); ++i) {
         double d = fabs((double)hD[i] - ref[i]);
         if (!(d <= 1e-3)) { if (first_bad < 0) first_bad = (int)i; ++bad; }
         if (d > maxerr || d != d) maxerr = d;
+        if (t.store_mode == 2) {             // 1 + two reduce-adds of the tile
+            double dr = fabs((double)hR[i] - (1.0 + 2.0 * ref[i]));
+            if (!(dr <= 2e-3)) { if (first_bad < 0) first_bad = (int)i; ++bad; }
+            if (dr > maxerr16) maxerr16 = dr;
+        }
         if (t.store_mode == 1) {
             double d16 = fabs((double)h2f16(hO[i], t.bf16) - ref[i]);
             double tol = 0.02 * fabs(ref[i]) + 0.02;
@@ -236,7 +281,7 @@ static bool run_test(const TestCfg& t) {
            t.expected ? "[expected]" : "[alt]     ", maxerr, maxerr16, bad);
     if (!ok) printf(" first_bad=(%d,%d) got=%f ref=%f", first_bad / N, first_bad % N, hD[first_bad], ref[first_bad]);
     printf("\n");
-    cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dO16);
+    cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dO16); cudaFree(dR);
     return ok;
 }
 
@@ -262,6 +307,14 @@ int main(int argc, char** argv) {
         {"ts_atmem_bkmajor_K128_N128",     true, 128, 128, false, true,  true,  0, 0, 0, 0, 0, 1024, 32, 8},
         {"tma_store_sw128_N128_bf16",      true, 128, 128, false, false, true,  1, 0, 1024, 32, 0, 1024, 32, 0},
         {"tma_store_sw128_N64_fp16",       true,  64,  64, false, false, false, 1, 0, 1024, 32, 0, 1024, 32, 0},
+        // fused backward: dQ[128 q x 64] = dS (A MN-major: smem holds dS^T [kv rows][128 q], two 64-column chunks)
+        //                                  * K (B MN-major [kv rows][64 d]); fp32 tile reduce-added by TMA
+        {"ss_amn_bmn_K128_N64_bf16",       true, 128,  64, true,  false, true,  0, 16384, 1024, 2048, 16384, 1024, 2048, 0, true},
+        {"ss_amn_bmn_K128_N64_fp16",       true, 128,  64, true,  false, false, 0, 16384, 1024, 2048, 16384, 1024, 2048, 0, true},
+        {"ss_amn_bkmajor_K64_N128_bf16",   true,  64, 128, false, false, true,  0, 8192, 1024, 2048, 0, 1024, 32, 0, true},
+        {"ss_amn_swapped_lbo_sbo",         false,128,  64, true,  false, true,  0, 1024, 16384, 2048, 16384, 1024, 2048, 0, true},
+        {"tma_reduce_add_f32_sw128_N64",   true, 128,  64, true,  false, true,  2, 0, 1024, 32, 16384, 1024, 2048, 0},
+        {"tma_reduce_add_f32_sw128_N128",  true, 128, 128, false, false, true,  2, 0, 1024, 32, 0, 1024, 32, 0},
     };
     int fails = 0;
     for (size_t i = 0; i < tests.size(); ++i) {

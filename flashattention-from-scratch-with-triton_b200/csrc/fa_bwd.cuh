@@ -37,6 +37,7 @@ struct BwdParams {
     unsigned int* sched_dkv;   // work counters (zeroed before launch) for the persistent kernels
     unsigned int* sched_dq;
     int sms;
+    int hc_dkv, hc_dq;         // heads per scheduling chunk (item_to_head_tile) for the K/V-tile and the Q-tile kernels
 };
 
 // Turn-taking between the two math warpgroups around the exp loop (named barriers 3/4, as in the forward):
@@ -146,7 +147,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     uint8_t* sK = smem + C::kOffRes;
     uint8_t* sV = sK + C::kTileBytes;
     uint8_t* sStage = smem + C::kOffStage;             // per stage: Q_i then dO_i
-    float* sStat = reinterpret_cast<float*>(smem + C::kOffStat);   // per slot: 128 x (-LSE*log2e), 128 x delta
+    float* sStat = reinterpret_cast<float*>(smem + C::kOffStat);   // per slot: 128 x (-LSE*log2e), 128 x (-delta)
     uint8_t* sOutV = C::kSepStage ? smem + C::kOffOut : sV;        // dV / dK staging for the TMA store
     uint8_t* sOutK = C::kSepStage ? smem + C::kOffOut + C::kTileBytes : sK;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
@@ -190,7 +191,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     // heavy first under causal.  With GQA the item walks the q tiles of every query head of the group, so the
     // reduction of dK/dV over the group happens in the TMEM accumulators (deterministic, no atomics).
     auto decode = [&](int item, int& bh, int& jt, int& i_start, int& n_it) {
-        bh = item / p.n_ktiles; jt = item % p.n_ktiles;     // bh = b * Hk + hk
+        item_to_head_tile(item, p.BH / p.G, p.n_ktiles, p.hc_dkv, bh, jt);     // bh = b * Hk + hk
         i_start = p.causal ? jt : 0;                       // first Q tile with a row >= kv_block_start (:341)
         n_it = max(p.n_qtiles - i_start, 0) * p.G;
     };
@@ -231,7 +232,8 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 float l[4];
                 if (vec_ok && q0 + 4 <= p.Sq) {
                     const float4 lv = __ldg(reinterpret_cast<const float4*>(p.lse + off));
-                    dl = __ldg(reinterpret_cast<const float4*>(p.delta + off));
+                    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.delta + off));
+                    dl = make_float4(-dv.x, -dv.y, -dv.z, -dv.w);          // the math warps add -delta (no negation in their loop)
                     l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
                 } else {
                     float d[4];
@@ -239,7 +241,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     for (int u = 0; u < 4; ++u) {
                         const bool in = q0 + u < p.Sq;                 // out-of-range query rows: P = exp2(-inf) = 0
                         l[u] = in ? __ldg(p.lse + off + u) : INFINITY;
-                        d[u] = in ? __ldg(p.delta + off + u) : 0.f;
+                        d[u] = in ? -__ldg(p.delta + off + u) : 0.f;
                     }
                     dl = make_float4(d[0], d[1], d[2], d[3]);
                 }
@@ -449,9 +451,9 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                             const float4 dl = lds128(stat + 512 + c * 4);
                             float d0, d1, d2, d3;        // dS = P o (dP - delta), packed: FADD2 + FMUL2
                             unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]),
-                                            fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), pack_f2(-dl.x, -dl.y))), d0, d1);
+                                            fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), pack_f2(dl.x, dl.y))), d0, d1);
                             unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]),
-                                            fadd2(pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]), pack_f2(-dl.z, -dl.w))), d2, d3);
+                                            fadd2(pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]), pack_f2(dl.z, dl.w))), d2, d3);
                             pk[i] = pack2<kBf16>(d0, d1); pk[i + 1] = pack2<kBf16>(d2, d3);
                         }
                         tmem_st16(tDPT + q * 16, pk);
@@ -562,7 +564,8 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
     // item -> (bh, q tile, number of kv tiles); descending q tile = heavy first under causal (:219 truncation)
     auto decode = [&](int item, int& bh, int& iq, int& n_it) {
-        bh = item / p.n_qtiles; iq = p.n_qtiles - 1 - (item % p.n_qtiles);
+        int qt; item_to_head_tile(item, p.BH, p.n_qtiles, p.hc_dq, bh, qt);
+        iq = p.n_qtiles - 1 - qt;
         n_it = fwd_tile_iters(iq * 128, 0, p.Sq, p.Sk, p.causal);
     };
     auto next_item = [&](uint32_t ix) -> int {           // whole warp

@@ -25,6 +25,7 @@ struct FwdParams {
     int G;                 // query heads per K/V head (GQA/MQA; 1 = the reference's layout): kv head = h / G
     int n_qblk;            // ceil(Sq / 256)
     int n_items;           // BH * n_qblk
+    int hc;                // heads per scheduling chunk (item_to_head_tile)
     int causal;
     float scale;           // softmax scale (1/sqrt(D) by default)
     float scale_log2;      // scale * log2(e)
@@ -143,8 +144,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 sched_item[slot] = item;
                 mbar_arrive_e(&sched_full[slot]);
                 if (item >= p.n_items) break;
-                const int bh = item / p.n_qblk;
-                const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;   // heavy (late) query blocks first
+                int bh, qt; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh, qt);
+                const int q0 = (p.n_qblk - 1 - qt) * 256;                   // heavy (late) query blocks first
                 const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
                 const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
                 const int n = max(n0, n1);
@@ -213,7 +214,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const int item = __shfl_sync(0xffffffffu, sched_item[slot], 0);   // warp-uniform for the compiler
                 mbar_arrive_e(&sched_empty[slot]);
                 if (item >= p.n_items) break;
-                const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
+                int bh_, qt; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh_, qt);
+                const int q0 = (p.n_qblk - 1 - qt) * 256;
                 const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
                 const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
                 const int n = max(n0, n1), nt = t ? n1 : n0;
@@ -296,7 +298,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const int item = __shfl_sync(0xffffffffu, sched_item[slot], 0);   // warp-uniform for the compiler
                 mbar_arrive_e(&sched_empty[slot]);
                 if (item >= p.n_items) break;
-                const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
+                int bh_, qt; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh_, qt);
+                const int q0 = (p.n_qblk - 1 - qt) * 256;
                 const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
                 const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
                 const int n = max(n0, n1);
@@ -374,8 +377,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(&sched_empty[slot]);
             if (item >= p.n_items) break;
-            const int bh = item / p.n_qblk;
-            const int q0 = (p.n_qblk - 1 - (item % p.n_qblk)) * 256;
+            int bh, qt; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh, qt);
+            const int q0 = (p.n_qblk - 1 - qt) * 256;
             const int nt = fwd_tile_iters(q0, t, p.Sq, p.Sk, p.causal);
             const int n_rounds = max(nt, fwd_tile_iters(q0, 1 - t, p.Sq, p.Sk, p.causal));
             if (nt == 0) {

@@ -35,6 +35,8 @@ class HostAttentionPipeline:
             self.bufs.append(dict(q=mk(S_q), k=mk(S_k), v=mk(S_k), do=mk(S_q), o=mk(S_q), dq=mk(S_q), dk=mk(S_k), dv=mk(S_k),
                                   lse=torch.empty(1, per, S_q, dtype=torch.float32, device=self.device),
                                   delta=torch.empty(1, per, S_q, dtype=torch.float32, device=self.device)))
+            if D == 64:                                  # fp32 dQ workspace of the fused backward (interface.py)
+                self.bufs[-1]["acc"] = torch.empty(1, per, S_q, D, dtype=torch.float32, device=self.device)
         self.s_in = torch.cuda.Stream(self.device)
         self.s_cmp = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
@@ -72,10 +74,17 @@ class HostAttentionPipeline:
                     rc = lib.fa_sm100_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), b["o"].data_ptr(), b["lse"].data_ptr(),
                                           1, n, S_q, S_k, D, dt, int(self.causal), scale, st)
                     interface._cabi.check("fa_sm100_fwd", rc)
-                    rc = lib.fa_sm100_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), b["o"].data_ptr(), do.data_ptr(),
-                                          b["lse"].data_ptr(), b["dq"].data_ptr(), b["dk"].data_ptr(), b["dv"].data_ptr(),
-                                          b["delta"].data_ptr(), 1, n, S_q, S_k, D, dt, int(self.causal), scale, st)
-                    interface._cabi.check("fa_sm100_bwd", rc)
+                    if "acc" in b and not interface.is_deterministic():
+                        rc = lib.fa_sm100_bwd_fused(q.data_ptr(), k.data_ptr(), v.data_ptr(), b["o"].data_ptr(), do.data_ptr(),
+                                                    b["lse"].data_ptr(), b["dq"].data_ptr(), b["dk"].data_ptr(), b["dv"].data_ptr(),
+                                                    b["delta"].data_ptr(), b["acc"].data_ptr(), 1, n, n, S_q, S_k, D, dt,
+                                                    int(self.causal), scale, None, st, 0)
+                        interface._cabi.check("fa_sm100_bwd_fused", rc)
+                    else:
+                        rc = lib.fa_sm100_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), b["o"].data_ptr(), do.data_ptr(),
+                                              b["lse"].data_ptr(), b["dq"].data_ptr(), b["dk"].data_ptr(), b["dv"].data_ptr(),
+                                              b["delta"].data_ptr(), 1, n, S_q, S_k, D, dt, int(self.causal), scale, st)
+                        interface._cabi.check("fa_sm100_bwd", rc)
                 cmp_done[c] = torch.cuda.Event(); cmp_done[c].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(cmp_done[c])

@@ -14,6 +14,8 @@ alias ``attention`` (BASELINE.json's spelling).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _cabi
@@ -88,6 +90,48 @@ def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_ca
     _cabi.check("fa_sm100_bwd_strided", rc)
 
 
+# Backward algorithm.  Head dim 64 defaults to the fused single-pass kernel (5 GEMMs and one exponential per score
+# element; dQ summed over kv tiles by TMA reduce-add in fp32, so its low-order bits depend on scheduling — like
+# PyTorch's own flash backward).  set_deterministic(True) or FA_SM100_DETERMINISTIC=1 selects the reference's
+# atomic-free two-kernel structure (code/My_FlashAttention_optimized.py:111-126) everywhere; head dim 128 always uses it.
+_deterministic = os.environ.get("FA_SM100_DETERMINISTIC", "0") not in ("", "0")
+
+
+def set_deterministic(flag: bool) -> bool:
+    """Select the bitwise-reproducible two-kernel backward for every head dim; returns the previous setting."""
+    global _deterministic
+    prev, _deterministic = _deterministic, bool(flag)
+    return prev
+
+
+def is_deterministic() -> bool:
+    return _deterministic
+
+
+def fused_backward_supported(Q) -> bool:
+    return Q.shape[-1] == 64
+
+
+BWD_FUSED, BWD_CONVERT = 8, 16
+
+
+def flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale=None, dq_acc=None, parts=0):
+    """delta -> fused dK/dV/dQ kernel -> dQ conversion (head dim 64).  dq_acc: optional fp32 [B,H,S_q,D] workspace."""
+    lib = _cabi.load()
+    B, H, S_q, D = Q.shape
+    S_k = K.shape[2]
+    if dq_acc is None:
+        dq_acc = torch.empty((B, H, S_q, D), dtype=torch.float32, device=Q.device)
+    assert dq_acc.dtype == torch.float32 and dq_acc.is_contiguous() and dq_acc.numel() == B * H * S_q * D
+    st = _strides(Q, K, V, O, dO, dQ, dK, dV)
+    with torch.cuda.device(Q.device):
+        rc = lib.fa_sm100_bwd_fused(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
+                                    LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
+                                    dq_acc.data_ptr(), B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                    float(sm_scale) if sm_scale is not None else 0.0, st, _stream(Q), int(parts))
+    _cabi.check("fa_sm100_bwd_fused", rc)
+
+
 def _empty_like_kernel(t):
     e = torch.empty_like(t)
     return e if tma_compatible(e) else torch.empty(t.shape, dtype=t.dtype, device=t.device)
@@ -98,7 +142,10 @@ def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None):
     B, H, S_q, D = Q.shape
     dQ, dK, dV = _empty_like_kernel(Q), _empty_like_kernel(K), _empty_like_kernel(V)      # reference :71-73
     delta = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
-    flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, BWD_DELTA | BWD_DQ | BWD_DKV, sm_scale)
+    if fused_backward_supported(Q) and not _deterministic:
+        flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale)
+    else:
+        flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, BWD_DELTA | BWD_DQ | BWD_DKV, sm_scale)
     return dQ, dK, dV
 
 

@@ -18,6 +18,7 @@
 #ifndef FA_SM100_H_
 #define FA_SM100_H_
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -81,6 +82,22 @@ int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* 
                        const float* lse, void* dq, void* dk, void* dv, float* delta,
                        int B, int H, int Sq, int Sk, int D, int dtype, int causal,
                        float sm_scale, void* stream, int parts);
+
+/* Fused single-pass backward, head dim 64 only: one kernel computes dK, dV and dQ with 5 GEMMs per
+ * (kv tile, q tile) pair and one exponential per score element, instead of the dQ + dK/dV kernel pair above
+ * (reference launcher code/My_FlashAttention_optimized.py:111-126: 7 GEMMs, two exponentials).  dQ partials are summed over kv
+ * tiles in an fp32 workspace `dq_acc` ([B,H,Sq,D] contiguous fp32, fa_sm100_bwd_fused_workspace() bytes, owned by the caller,
+ * need not be initialised) by TMA reduce-add, then scaled and converted into `dq`.  Runs delta -> fused kernel -> convert.
+ * dK/dV are bitwise reproducible; dQ's fp32 summation order over kv tiles depends on scheduling (use fa_sm100_bwd_strided
+ * for the deterministic path).  Arguments otherwise as fa_sm100_bwd_strided; D != 64 returns FA_ERR_HEADDIM.
+ * parts: 0 = everything, else a mask of FA_BWD_DELTA (delta + zeroing of dq_acc), FA_BWD_FUSED, FA_BWD_CONVERT (per-kernel timing). */
+#define FA_BWD_FUSED 8
+#define FA_BWD_CONVERT 16
+size_t fa_sm100_bwd_fused_workspace(int B, int H, int Sq, int D);
+int fa_sm100_bwd_fused(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                       const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_acc,
+                       int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal,
+                       float sm_scale, const long long* strides, void* stream, int parts);
 
 /* delta = rowsum(dout * o) alone (the preprocess step of the backward; kernel :210-211). */
 int fa_sm100_delta(const void* o, const void* dout, float* delta,

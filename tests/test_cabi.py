@@ -57,6 +57,11 @@ def test_argument_validation_without_gpu(lib):
     bad = (ctypes.c_longlong * 12)(*([128 * 64 * 2, 128 * 64, 64] * 3 + [128 * 64 * 2, 128 * 64, 60]))   # o row stride 60: not 16-byte
     assert lib.fa_sm100_fwd_strided(p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, bad, None) == -8
     assert lib.fa_sm100_fwd_strided(p, p, p, p, p, 1, 6, 4, 128, 128, 64, 1, 0, 0.0, None, None) == -4   # Hk must divide H
+    fused = lambda D=64, acc=p: lib.fa_sm100_bwd_fused(p, p, p, p, p, p, p, p, p, p, acc, 1, 2, 2, 128, 128, D, 1, 1, 0.0, None, None, 0)
+    assert fused(D=128) == -3 and b"fused" in lib.fa_last_error()          # TMEM budget: head dim 64 only
+    assert fused(acc=None) == -1
+    assert lib.fa_sm100_bwd_fused_workspace(2, 4, 256, 64) == 2 * 4 * 256 * 64 * 4
+    assert lib.fa_sm100_bwd_fused_workspace(2, 4, 256, 128) == 0
     assert lib.fa_sm100_delta(p, None, p, 1, 1, 128, 64, 1, None) == -1
     assert lib.fa_sm100_merge(p, p, p, None, 1, 1, 128, 64, 1, 128, 0, None) == -1
     assert lib.fa_sm100_merge(p, p, p, p, 1, 1, 128, 64, 1, 128, 64, None) == -4
