@@ -31,37 +31,54 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 // Element strides (batch, head, row) of a [B,H,S,D] tensor whose D is contiguous
 struct RowStrides { long long b, h, r; };
 
+// Four rows per thread with all eight 16-byte loads issued before the first use: these launches are a few tens of MB,
+// so what counts is bytes in flight per SM in a single wave, not the loop.
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(256) fa_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ dout,
                                                        float* __restrict__ delta, long long rows, int H, int Sq,
                                                        RowStrides so, RowStrides sd, float4* __restrict__ zero_acc) {
     constexpr int TPR = D / 8;                       // threads per row
     constexpr int RPB = 256 / TPR;                   // rows per block per step
+    constexpr int U = 4;                             // rows per thread per iteration
     const int sub = threadIdx.x % TPR;
-    for (long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row < rows; row += (long long)gridDim.x * RPB) {
-        const long long bh = row / Sq, sq = row % Sq, bb = bh / H, hh = bh % H;
-        const uint4 a = __ldg(o + ((bb * so.b + hh * so.h + sq * so.r) >> 3) + sub);
-        const uint4 b = __ldg(dout + ((bb * sd.b + hh * sd.h + sq * sd.r) >> 3) + sub);
-        float fa_[8], fb[8];
-        unpack8<kBf16>(a, fa_); unpack8<kBf16>(b, fb);
-        float acc = 0.f;
+    const long long stride = (long long)gridDim.x * RPB;
+    for (long long row0 = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row0 < rows; row0 += stride * U) {
+        uint4 a[U], b[U];
         #pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(fa_[i], fb[i], acc);
+        for (int u = 0; u < U; ++u) {
+            const long long row = row0 + u * stride;
+            if (row < rows) {
+                const long long bh = row / Sq, sq = row % Sq, bb = bh / H, hh = bh % H;
+                a[u] = __ldg(o + ((bb * so.b + hh * so.h + sq * so.r) >> 3) + sub);
+                b[u] = __ldg(dout + ((bb * sd.b + hh * sd.h + sq * sd.r) >> 3) + sub);
+            }
+        }
         #pragma unroll
-        for (int off = TPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(row_group_mask<TPR>(), acc, off);
-        if (sub == 0) delta[row] = acc;
-        if (zero_acc) {                              // fused backward: clear the fp32 dQ accumulator [rows, D] on the way
-            zero_acc[row * (D / 4) + sub * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-            zero_acc[row * (D / 4) + sub * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < U; ++u) {
+            const long long row = row0 + u * stride;
+            if (row < rows) {                        // uniform over the TPR lanes of a row
+                float fa_[8], fb[8];
+                unpack8<kBf16>(a[u], fa_); unpack8<kBf16>(b[u], fb);
+                float acc = 0.f;
+                #pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fmaf(fa_[i], fb[i], acc);
+                #pragma unroll
+                for (int off = TPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(row_group_mask<TPR>(), acc, off);
+                if (sub == 0) delta[row] = acc;
+                if (zero_acc) {                      // fused backward: clear the fp32 dQ accumulator [rows, D] on the way
+                    zero_acc[row * (D / 4) + sub * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    zero_acc[row * (D / 4) + sub * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
         }
     }
 }
 
 inline int launch_delta(const void* o, const void* dout, float* delta, long long rows, int H, int Sq, RowStrides so,
                         RowStrides sd, int D, int dtype, int sms, cudaStream_t st, float* zero_acc = nullptr) {
-    const int rpb = 256 / (D / 8);
+    const int rpb = 256 / (D / 8) * 4;
     long long blocks = (rows + rpb - 1) / rpb;
-    const long long cap = (long long)sms * 16;
+    const long long cap = (long long)sms * 8;
     if (blocks > cap) blocks = cap;
     const uint4* o4 = (const uint4*)o; const uint4* d4 = (const uint4*)dout;
     if (D == 64) { if (dtype) fa_delta_kernel<64, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc);

@@ -45,6 +45,14 @@ struct BwdParams {
 #ifndef FA_BWD_STAGGER
 #define FA_BWD_STAGGER 0   // measured: no gain (both warpgroups share one tile, the MMA wait dominates); kept as a knob
 #endif
+// Of every 16 score columns, this many (0, 4, 8) take their exp2 from the FMA-pipe polynomial (ex2_poly2) instead of MUFU: the
+// exp phase of both backward loops queues on the MUFU unit (ncu: stall_mio) while the FMA pipe idles.  Measured A/B
+// (profiles/r01_ab_bwd_poly.txt): 4 is best at D = 64 (-5..-7 %), 8 for the dK/dV kernel at D = 128 (-3..-4 %), dQ at 128 is flat.
+#ifdef FA_BWD_POLY
+template <int D> struct BwdPoly { static constexpr int kDkv = FA_BWD_POLY, kDq = FA_BWD_POLY; };
+#else
+template <int D> struct BwdPoly { static constexpr int kDkv = (D == 128) ? 8 : 4, kDq = 4; };
+#endif
 constexpr int kBwdThreads = 384;
 constexpr int kBwdRegsCompute = 208, kBwdRegsOther = 80;
 constexpr float kLog2e = 1.44269504088896340736f;
@@ -415,10 +423,15 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     #pragma unroll
                     for (int c = 0; c < 64; c += 4) {
                         const float4 nl = lds128(stat + c * 4);
-                        float x0, x1, x2, x3;
-                        unpack_f2(ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, pack_f2(nl.x, nl.y)), x0, x1);
-                        unpack_f2(ffma2(pack_u2(s[c >> 5][(c & 31) + 2], s[c >> 5][(c & 31) + 3]), c2v, pack_f2(nl.z, nl.w)), x2, x3);
-                        pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1); pv[c + 2] = ex2_approx(x2); pv[c + 3] = ex2_approx(x3);
+                        const uint64_t xa = ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, pack_f2(nl.x, nl.y));
+                        const uint64_t xb = ffma2(pack_u2(s[c >> 5][(c & 31) + 2], s[c >> 5][(c & 31) + 3]), c2v, pack_f2(nl.z, nl.w));
+                        if ((c & 15) < BwdPoly<D>::kDkv) {
+                            ex2_poly2(xa, pv[c], pv[c + 1]); ex2_poly2(xb, pv[c + 2], pv[c + 3]);
+                        } else {
+                            float x0, x1, x2, x3;
+                            unpack_f2(xa, x0, x1); unpack_f2(xb, x2, x3);
+                            pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1); pv[c + 2] = ex2_approx(x2); pv[c + 3] = ex2_approx(x3);
+                        }
                     }
                     if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
                 }
@@ -694,9 +707,14 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     const uint64_t c2v = pack_f2(c2, c2), nlv = pack_f2(nl, nl);
                     #pragma unroll
                     for (int c = 0; c < 64; c += 2) {
-                        float x0, x1;
-                        unpack_f2(ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, nlv), x0, x1);
-                        pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1);
+                        const uint64_t xa = ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, nlv);
+                        if ((c & 15) < BwdPoly<D>::kDq) {
+                            ex2_poly2(xa, pv[c], pv[c + 1]);
+                        } else {
+                            float x0, x1;
+                            unpack_f2(xa, x0, x1);
+                            pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1);
+                        }
                     }
                     if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
                 }

@@ -14,9 +14,10 @@
 // the delta preprocess kernel.  Summation order over kv tiles depends on scheduling, so dQ is not bitwise
 // reproducible run to run (dK, dV are); the two-kernel path stays available as the deterministic mode.
 //
-// TMEM (512 columns): S^T [0,128)  dP^T / dS^T [128,256)  dV [256,320)  dK [320,384)  dQ partial [384,448)
-// P^T 16-bit [448,512).  P^T has its own region, so S^T is released as soon as it is in registers and S^T(i+1) runs
-// under the exp of tile i; dQ(i) is drained by the math warps in iteration i+1 between their P and dS phases.
+// TMEM (512 columns): S^T [0,128)  dP^T / dS^T [128,256)  dV [256,320)  dK [320,384)  dQ partial | P^T [384,448) (they take
+// turns)  K [448,480)  V [480,512) (16-bit copies of the resident tiles: A operands of the score MMAs).  P^T does not
+// overwrite S^T, so S^T is released as soon as it is in registers and S^T(i+1) runs under the exp of tile i; dQ(i) is
+// drained by the math warps in iteration i+1 right before they store P^T(i+1).
 // Warps: 0-7 math (two warpgroups, 64 score columns each), 8 MMA issuer, 9 TMA producer + scheduler,
 // 10 statistics loader, 11 dQ reducer.
 #pragma once
@@ -33,6 +34,15 @@ namespace fa {
 // phase of the loop is bound by the MUFU queue (ncu: stall_mio) while the FMA pipe idles; 4 measured best (-2..-7 %)
 #ifndef FA_FUSED_POLY
 #define FA_FUSED_POLY 4
+#endif
+// the two math warpgroups take turns on the exp phase (named barriers 3/4): while one is on the MUFU unit the other runs
+// its FMA / LDS / TMEM-bound dS phase
+#ifndef FA_FUSED_STAGGER
+#define FA_FUSED_STAGGER 1      // measured: -3..-4 %
+#endif
+// MMA issue order after dS(i): dK(i), dP^T(i+1), dQ(i) instead of dK(i), dQ(i), dP^T(i+1)
+#ifndef FA_FUSED_DP_FIRST
+#define FA_FUSED_DP_FIRST 0
 #endif
 
 template <int D> struct FusedCfg {
@@ -64,6 +74,15 @@ __device__ __forceinline__ void issue_dq_partial(uint32_t d_tmem, uint32_t ds_ad
                   idesc, k > 0);
 }
 
+// score-tile MMA with the resident operand in TMEM: D[tmem 128x128] = A[tmem: 128 lanes x D 16-bit = D/2 columns] * B[smem 128 x D, K-major]^T
+template <int D, bool kBf16>
+__device__ __forceinline__ void issue_scores_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr) {
+    constexpr uint32_t idesc = make_idesc(kBf16, false, false, 128, 128);
+    #pragma unroll
+    for (int k = 0; k < D / 16; ++k)
+        umma_ts_e(d_tmem, a_tmem + k * 8, make_smem_desc(b_addr + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024), idesc, k > 0);
+}
+
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -87,7 +106,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     uint64_t* acc_full = bars + 6;      uint64_t* s_taken = bars + 7;     // S^T(i) is in registers
     uint64_t* acc_empty = bars + 8;     uint64_t* kv_free = bars + 22;       // [2]
     uint64_t* sched_full = bars + 10;   uint64_t* sched_empty = bars + 12;   // [2] each
-    uint64_t* pv_free = bars + 14;      // dV(i) has consumed P^T(i)
+    uint64_t* kvt_full = bars + 14;     // K (warpgroup A) and V (warpgroup B) of the item are in TMEM (256 math threads)
     uint64_t* dq_full = bars + 15;      // dQ partial of tile i is in TMEM (and dS^T(i) in smem is no longer read)
     uint64_t* dqs_full = bars + 16;     // dQ partial staged in smem (256 math threads)
     uint64_t* dqs_empty = bars + 17;    // the reduce has read the staging
@@ -106,7 +125,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_free[i], 1); }
         mbar_init(s_full, 1); mbar_init(dp_full, 1);
         mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(acc_full, 1); mbar_init(acc_empty, 256);
-        mbar_init(s_taken, 256); mbar_init(pv_free, 1); mbar_init(dq_full, 1);
+        mbar_init(s_taken, 256); mbar_init(kvt_full, 256); mbar_init(dq_full, 1);
         mbar_init(dqs_full, 256); mbar_init(dqs_empty, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 11); }
         for (int i = 0; i < C::kStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&do_full[i], 1); mbar_init(&stage_empty[i], 1); }
@@ -118,8 +137,13 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 256 + D, kColDQ = 256 + 2 * D, kColP = 256 + 3 * D;
-    static_assert(kColP + 64 <= 512, "TMEM budget");
+    // dQ partial (fp32, q lanes) and P^T (16-bit, kv lanes) take turns in ONE region: dQ(i-1) is drained right before P^T(i)
+    // is written, dV(i) has consumed P^T(i) before the in-order MMA pipe reaches dQ(i).  The 64 columns this saves hold K and V
+    // (16-bit, kv lanes) as the A operands of the two score MMAs: 32 KB less shared-memory operand traffic per tile — the
+    // kernel is bound by the shared-memory pipe (ncu: LSU + tensor-core wavefronts ~ 85 % of peak).
+    constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 256 + D, kColDQ = 256 + 2 * D, kColP = kColDQ;
+    constexpr uint32_t kColKT = 256 + 3 * D, kColVT = kColKT + D / 2;
+    static_assert(kColVT + D / 2 <= 512, "TMEM budget");
 
     // item -> (batch*Hk + kv head, kv tile, first q tile, iterations); with GQA the item walks the q tiles of every
     // query head of the group (dK/dV reduce over the group in TMEM)
@@ -282,16 +306,15 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             auto dofull = [&](uint32_t g) { mbar_wait(&do_full[g % C::kStages], (g / C::kStages) & 1, 623); };
             auto stage_addr = [&](uint32_t g) { return aSt + (g % C::kStages) * C::kStageBytes; };
             const uint32_t kb = ix & 1;
-            const uint32_t aK = aKV + kb * 2 * C::kTileBytes, aV = aK + C::kTileBytes;
-            mbar_wait(&k_full[kb], (ix >> 1) & 1, 620);
-            if (n_it == 0) mbar_wait(&v_full[kb], (ix >> 1) & 1, 622);
+            const uint32_t aK = aKV + kb * 2 * C::kTileBytes;         // smem K: B operand of the dQ MMA
+            mbar_wait(kvt_full, ix & 1, 620);                         // K, V of this item copied into TMEM (implies k_full, v_full)
+            tc_fence_after();
             if (n_it > 0) {
                 if (gi > 0) mbar_wait(s_taken, (gi - 1) & 1, 627);      // the previous item's last S^T is in registers
                 qfull(git); tc_fence_after();
-                issue_scores<D, kBf16>(tmem + kColST, aK, stage_addr(git)); tc_commit_e(s_full);
-                mbar_wait(&v_full[kb], (ix >> 1) & 1, 622);
+                issue_scores_ts<D, kBf16>(tmem + kColST, tmem + kColKT, stage_addr(git)); tc_commit_e(s_full);
                 dofull(git); tc_fence_after();
-                issue_scores<D, kBf16>(tmem + kColDPT, aV, stage_addr(git) + C::kTileBytes); tc_commit_e(dp_full);
+                issue_scores_ts<D, kBf16>(tmem + kColDPT, tmem + kColVT, stage_addr(git) + C::kTileBytes); tc_commit_e(dp_full);
             }
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it, gt = git + it;
@@ -300,21 +323,24 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                 if (more) {                                              // S^T(i+1) under the exp of tile i
                     mbar_wait(s_taken, g & 1, 627);
                     qfull(gt + 1); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColST, aK, stage_addr(gt + 1)); tc_commit_e(s_full);
+                    issue_scores_ts<D, kBf16>(tmem + kColST, tmem + kColKT, stage_addr(gt + 1)); tc_commit_e(s_full);
                 }
                 mbar_wait(p_full, g & 1, 624);
                 if (it == 0) mbar_wait(acc_empty, (ix & 1) ^ 1, 629);    // previous item's dV/dK/dQ drained from TMEM
                 tc_fence_after();
                 issue_grad<D, kBf16, false>(tmem + kColDV, tmem + kColP, adO, it > 0);      // dV += P^T dO_i
-                tc_commit_e(pv_free);
                 mbar_wait(ds_full, g & 1, 626); tc_fence_after();
                 issue_grad<D, kBf16>(tmem + kColDK, tmem + kColDPT, aQ, it > 0);            // dK += dS^T Q_i
                 tc_commit_e(&stage_empty[gt % C::kStages]);
+                if (FA_FUSED_DP_FIRST && more) {
+                    dofull(gt + 1); tc_fence_after();
+                    issue_scores_ts<D, kBf16>(tmem + kColDPT, tmem + kColVT, stage_addr(gt + 1) + C::kTileBytes); tc_commit_e(dp_full);   // dP^T(i+1)
+                }
                 if (!(FA_FUSED_SKIP & 2)) issue_dq_partial<D, kBf16>(tmem + kColDQ, aDS, aK);    // dQ_i partial = dS K
                 tc_commit_e(dq_full);
-                if (more) {
+                if (!FA_FUSED_DP_FIRST && more) {
                     dofull(gt + 1); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColDPT, aV, stage_addr(gt + 1) + C::kTileBytes); tc_commit_e(dp_full);   // dP^T(i+1)
+                    issue_scores_ts<D, kBf16>(tmem + kColDPT, tmem + kColVT, stage_addr(gt + 1) + C::kTileBytes); tc_commit_e(dp_full);   // dP^T(i+1)
                 }
             }
             if (n_it == 0) mbar_wait(acc_empty, (ix & 1) ^ 1, 629);
@@ -334,9 +360,11 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         const uint32_t tDQ = tmem + lane_field + kColDQ + h * 32;       // my 32 of the 64 dQ columns (lane = q row)
         const uint32_t sDSh = smem_u32(sDS) + h * 16384;                // my 64 q columns = one swizzled chunk
         const uint32_t sDQh = smem_u32(sDQ) + h * 16384;                // my fp32 box
+        const uint32_t tKV = tmem + lane_field + (h ? kColVT : kColKT); // warpgroup A keeps K in TMEM, warpgroup B keeps V
         const float c2 = p.scale_log2;
         uint32_t gi = 0;
         bool store_pending = false;
+        if (FA_FUSED_STAGGER && h == 1) named_bar_arrive(3, 256);       // warpgroup A takes the first turn
         // the dV/dK store of the previous item reads the staging that aliases the dS^T tile
         auto staging_free = [&]() {
             if (store_pending) {
@@ -359,8 +387,29 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             fence_proxy_async_smem();
             mbar_arrive(dqs_full);
         };
+        // K / V tile of item ix: shared memory (row r = 128 swizzled bytes) -> 32 TMEM columns of lane r.  Called once the
+        // previous item's MMAs are complete (acc_full), i.e. nothing reads the TMEM copies any more.
+        auto copy_kv = [&](uint32_t ix) {
+            const uint32_t kb = ix & 1;
+            mbar_wait(h ? &v_full[kb] : &k_full[kb], (ix >> 1) & 1, 637);
+            const uint32_t src = smem_u32(sKV) + kb * 2 * C::kTileBytes + h * C::kTileBytes;
+            #pragma unroll
+            for (int q = 0; q < D / 32; ++q) {
+                uint32_t w[16];
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = lds128(src + sw128_offset(r, q * 4 + j));
+                    w[4 * j] = __float_as_uint(v.x); w[4 * j + 1] = __float_as_uint(v.y);
+                    w[4 * j + 2] = __float_as_uint(v.z); w[4 * j + 3] = __float_as_uint(v.w);
+                }
+                tmem_st16(tKV + q * 16, w);
+            }
+            tc_wait_st(); tc_fence_before();
+            mbar_arrive(kvt_full);
+        };
+        int item = next_item(0);
+        if (item < n_items) copy_kv(0);
         for (uint32_t ix = 0;; ++ix) {
-            const int item = next_item(ix);
             if (item >= n_items) break;
             int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
             const int kv_g = jt * 128 + r;
@@ -381,6 +430,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                     tc_wait_ld();
                     tc_fence_before();
                     mbar_arrive(s_taken);
+                    if (FA_FUSED_STAGGER) named_bar_sync(3 + h, 256);
                     const uint64_t c2v = pack_f2(c2, c2);
                     #pragma unroll
                     for (int c = 0; c < 64; c += 4) {
@@ -392,16 +442,22 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                         } else {
                             float x0, x1, x2, x3;
                             unpack_f2(xa, x0, x1); unpack_f2(xb, x2, x3);
-                            pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1); pv[c + 2] = ex2_approx(x2); pv[c + 3] = ex2_approx(x3);
+                            if (FA_FUSED_STAGGER) {
+                                pv[c] = ex2_approx_ordered(x0); pv[c + 1] = ex2_approx_ordered(x1);
+                                pv[c + 2] = ex2_approx_ordered(x2); pv[c + 3] = ex2_approx_ordered(x3);
+                            } else {
+                                pv[c] = ex2_approx(x0); pv[c + 1] = ex2_approx(x1); pv[c + 2] = ex2_approx(x2); pv[c + 3] = ex2_approx(x3);
+                            }
                         }
                     }
+                    if (FA_FUSED_STAGGER) named_bar_arrive(4 - h, 256);
                 }
                 if (p.causal && q0 < kv_g) {                 // tile straddles the diagonal: keep q >= kv only
                     const int cmin = kv_g - q0;
                     #pragma unroll
                     for (int c = 0; c < 64; ++c) if (c < cmin) pv[c] = 0.f;
                 }
-                if (g > 0) { mbar_wait(pv_free, (g - 1) & 1, 636); tc_fence_after(); }     // dV(i-1) has read P^T(i-1)
+                if (it > 0) drain_dq(g - 1);                 // frees the shared TMEM region (its MMAs finished during the exp)
                 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     uint32_t pk[16];
@@ -411,7 +467,6 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                 }
                 tc_wait_st(); tc_fence_before();
                 mbar_arrive(p_full);
-                if (it > 0) drain_dq(g - 1);                 // dQ(i-1): its MMAs finished long ago
                 mbar_wait(dp_full, g & 1, 632);
                 tc_fence_after();
                 {
@@ -450,6 +505,8 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             if (n_it > 0) drain_dq(gi - 1);
             // ---- epilogue: dV, dK*scale -> 16-bit -> smem staging (over the dS^T tile) -> TMA store
             mbar_wait(acc_full, ix & 1, 633); tc_fence_after();
+            const int item_next = next_item(ix + 1);         // before the epilogue: the MMA warp starts the next item's score
+            if (item_next < n_items) copy_kv(ix + 1);        // MMAs under it
             staging_free();
             stage_grad_half<D, kBf16>(tmem + lane_field + kColDV, sOutV, r, h, 1.0f, n_it == 0);
             stage_grad_half<D, kBf16>(tmem + lane_field + kColDK, sOutK, r, h, p.scale, n_it == 0);
@@ -463,6 +520,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                 tma_store_commit();
             }
             store_pending = true;
+            item = item_next;
         }
         if (tid == 0) tma_store_wait_all0();
     }
@@ -471,20 +529,34 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
-// dq[b,h,s,:] = scale * accumulator[b,h,s,:]  (fp32 contiguous [B*H, Sq, D] -> 16-bit, any strides)
+// dq[b,h,s,:] = scale * accumulator[b,h,s,:]  (fp32 contiguous [B*H, Sq, D] -> 16-bit, any strides); four rows per thread,
+// loads first (the accumulator usually still sits in L2 after the reduce-adds)
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(256) fa_dq_convert_kernel(const float4* __restrict__ acc, uint4* __restrict__ dq, long long rows,
                                                             int H, int Sq, RowStrides sd, float scale) {
     constexpr int TPR = D / 8;
     constexpr int RPB = 256 / TPR;
+    constexpr int U = 4;
     const int sub = threadIdx.x % TPR;
-    for (long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row < rows; row += (long long)gridDim.x * RPB) {
-        const long long bh = row / Sq, sq = row % Sq, bb = bh / H, hh = bh % H;
-        const float4 a = __ldg(acc + row * (D / 4) + sub * 2), b = __ldg(acc + row * (D / 4) + sub * 2 + 1);
-        uint4 o;
-        o.x = pack2<kBf16>(a.x * scale, a.y * scale); o.y = pack2<kBf16>(a.z * scale, a.w * scale);
-        o.z = pack2<kBf16>(b.x * scale, b.y * scale); o.w = pack2<kBf16>(b.z * scale, b.w * scale);
-        dq[((bb * sd.b + hh * sd.h + sq * sd.r) >> 3) + sub] = o;
+    const long long stride = (long long)gridDim.x * RPB;
+    for (long long row0 = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row0 < rows; row0 += stride * U) {
+        float4 a[U], b[U];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = row0 + u * stride;
+            if (row < rows) { a[u] = __ldg(acc + row * (D / 4) + sub * 2); b[u] = __ldg(acc + row * (D / 4) + sub * 2 + 1); }
+        }
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = row0 + u * stride;
+            if (row < rows) {
+                const long long bh = row / Sq, sq = row % Sq, bb = bh / H, hh = bh % H;
+                uint4 o;
+                o.x = pack2<kBf16>(a[u].x * scale, a[u].y * scale); o.y = pack2<kBf16>(a[u].z * scale, a[u].w * scale);
+                o.z = pack2<kBf16>(b[u].x * scale, b[u].y * scale); o.w = pack2<kBf16>(b[u].z * scale, b[u].w * scale);
+                dq[((bb * sd.b + hh * sd.h + sq * sd.r) >> 3) + sub] = o;
+            }
+        }
     }
 }
 
@@ -505,9 +577,9 @@ int launch_bwd_fused_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !(parts & 16)) return (int)e;
     const long long rows = (long long)p.BH * p.Sq;
-    const int rpb = 256 / (D / 8);
+    const int rpb = 256 / (D / 8) * 4;
     long long blocks = (rows + rpb - 1) / rpb;
-    const long long cap = (long long)p.sms * 16;
+    const long long cap = (long long)p.sms * 8;
     if (blocks > cap) blocks = cap;
     fa_dq_convert_kernel<D, kBf16><<<(int)blocks, 256, 0, st>>>((const float4*)acc, (uint4*)dq, rows, p.H, p.Sq, s_dq, p.scale);
     return (int)cudaGetLastError();

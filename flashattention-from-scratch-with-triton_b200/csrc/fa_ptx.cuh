@@ -24,6 +24,10 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 __device__ __forceinline__ float ex2_approx(float x) {
     float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
+// ordered variant: stays between the named barriers that bracket a warpgroup's turn on the MUFU unit
+__device__ __forceinline__ float ex2_approx_ordered(float x) {
+    float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
 __device__ __forceinline__ float lg2_approx(float x) {
     float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
