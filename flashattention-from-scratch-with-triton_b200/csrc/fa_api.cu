@@ -140,16 +140,21 @@ template <typename K> cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-template <int D, bool kBf16>
-int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
-               const FwdParams& p, int grid, cudaStream_t st) {
+template <int D, bool kBf16, bool kRanges>
+int launch_fwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
+                 const FwdParams& p, int grid, cudaStream_t st) {
     static std::once_flag once; static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = set_smem(fa_fwd_kernel<D, kBf16>, FwdCfg<D>::kSmemBytes); });
+    std::call_once(once, [] { attr_err = set_smem(fa_fwd_kernel<D, kBf16, kRanges>, FwdCfg<D>::kSmemBytes); });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(fwd smem)");
-    fa_fwd_kernel<D, kBf16><<<grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mo, p);
+    fa_fwd_kernel<D, kBf16, kRanges><<<grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mo, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd_kernel launch");
+}
+template <int D, bool kBf16>
+int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
+               const FwdParams& p, int grid, cudaStream_t st) {
+    return p.row_lo ? launch_fwd_t<D, kBf16, true>(mq, mk, mv, mo, p, grid, st) : launch_fwd_t<D, kBf16, false>(mq, mk, mv, mo, p, grid, st);
 }
 
 }  // namespace
@@ -183,7 +188,14 @@ int fa_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* ls
 int fa_sm100_fwd_strided(const void* q, const void* k, const void* v, void* o, float* lse,
                          int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                          const long long* strides, void* stream) {
+    return fa_sm100_fwd_ranges(q, k, v, o, lse, B, H, Hk, Sq, Sk, D, dtype, causal, sm_scale, strides, nullptr, nullptr, stream);
+}
+
+int fa_sm100_fwd_ranges(const void* q, const void* k, const void* v, void* o, float* lse,
+                        int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                        const long long* strides, const int* row_lo, const int* row_hi, void* stream) {
     if (!q || !k || !v || !o || !lse) return fail(FA_ERR_NULL, "null tensor pointer");
+    if ((row_lo == nullptr) != (row_hi == nullptr)) return fail(FA_ERR_NULL, "row_lo and row_hi must be given together");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
     if (Hk <= 0 || H % Hk) return fail(FA_ERR_SHAPE, "K/V heads %d must divide query heads %d", Hk, H);
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return fail(FA_ERR_ALIGN, "q/k/v/o must be 16-byte aligned");
@@ -206,6 +218,7 @@ int fa_sm100_fwd_strided(const void* q, const void* k, const void* v, void* o, f
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse;
+    p.row_lo = row_lo; p.row_hi = row_hi;
     p.sched = dev->sched_ring + (g_sched_next.fetch_add(1) % kSchedRing);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(p.sched, 0, sizeof(unsigned int), st);
@@ -257,7 +270,18 @@ int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void
                          const float* lse, void* dq, void* dk, void* dv, float* delta,
                          int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                          const long long* strides, void* stream, int parts) {
+    return fa_sm100_bwd_ranges(q, k, v, o, dout, lse, dq, dk, dv, delta, B, H, Hk, Sq, Sk, D, dtype, causal, sm_scale, strides,
+                               nullptr, nullptr, nullptr, nullptr, stream, parts);
+}
+
+int fa_sm100_bwd_ranges(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                        const float* lse, void* dq, void* dk, void* dv, float* delta,
+                        int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                        const long long* strides, const int* row_lo, const int* row_hi, const int* col_lo, const int* col_hi,
+                        void* stream, int parts) {
     if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta) return fail(FA_ERR_NULL, "null tensor pointer");
+    if (!row_lo != !row_hi || !row_lo != !col_lo || !row_lo != !col_hi)
+        return fail(FA_ERR_NULL, "row_lo, row_hi, col_lo and col_hi must be given together");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
     if (Hk <= 0 || H % Hk) return fail(FA_ERR_SHAPE, "K/V heads %d must divide query heads %d", Hk, H);
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dout) ||
@@ -292,6 +316,7 @@ int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;
+    p.row_lo = row_lo; p.row_hi = row_hi; p.col_lo = col_lo; p.col_hi = col_hi;
     p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
     p.sms = dev->sms;
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
@@ -353,6 +378,7 @@ int fa_sm100_bwd_fused(const void* q, const void* k, const void* v, const void* 
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;
+    p.row_lo = p.row_hi = p.col_lo = p.col_hi = nullptr;
     p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
     p.sms = dev->sms;
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);

@@ -38,6 +38,11 @@ struct BwdParams {
     unsigned int* sched_dq;
     int sms;
     int hc_dkv, hc_dq;         // heads per scheduling chunk (item_to_head_tile) for the K/V-tile and the Q-tile kernels
+    // Optional range masks (FwdParams): row_lo/row_hi [B, Sq] = keys visible to a query row (used by the dQ kernel);
+    // col_lo/col_hi [B, Sk] = queries that see a key row (the same mask seen from the K/V side, used by the dK/dV kernel).
+    // All four non-decreasing along the sequence; NULL = unrestricted.
+    const int* row_lo; const int* row_hi;
+    const int* col_lo; const int* col_hi;
 };
 
 // Turn-taking between the two math warpgroups around the exp loop (named barriers 3/4, as in the forward):
@@ -54,7 +59,10 @@ template <int D> struct BwdPoly { static constexpr int kDkv = FA_BWD_POLY, kDq =
 template <int D> struct BwdPoly { static constexpr int kDkv = (D == 128) ? 8 : 4, kDq = 4; };
 #endif
 constexpr int kBwdThreads = 384;
-constexpr int kBwdRegsCompute = 208, kBwdRegsOther = 80;
+// setmaxnreg split (2 math warpgroups + 1 warpgroup of MMA / TMA / statistics warps) of the CTA's 384 x 168 registers:
+// 2 * compute + other <= 504, or setmaxnreg.inc never returns
+template <int D> struct BwdRegs { static constexpr int kCompute = 208, kOther = 80; };
+static_assert(2 * BwdRegs<64>::kCompute + BwdRegs<64>::kOther <= 504 && 2 * BwdRegs<128>::kCompute + BwdRegs<128>::kOther <= 504, "register pool");
 constexpr float kLog2e = 1.44269504088896340736f;
 
 template <int D> struct BwdCfg {
@@ -198,10 +206,16 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     // item -> (batch*Hk + kv head, kv tile, first q tile, q tiles per query head, iterations); ascending kv tile =
     // heavy first under causal.  With GQA the item walks the q tiles of every query head of the group, so the
     // reduction of dK/dV over the group happens in the TMEM accumulators (deterministic, no atomics).
-    auto decode = [&](int item, int& bh, int& jt, int& i_start, int& n_it) {
+    auto decode = [&](int item, int& bh, int& jt, int& i_start, int& i_end, int& n_it) {
         item_to_head_tile(item, p.BH / p.G, p.n_ktiles, p.hc_dkv, bh, jt);     // bh = b * Hk + hk
         i_start = p.causal ? jt : 0;                       // first Q tile with a row >= kv_block_start (:341)
-        n_it = max(p.n_qtiles - i_start, 0) * p.G;
+        i_end = p.n_qtiles;
+        if (p.col_lo) {                                    // range mask: q tiles [first query of the first kv row, last query of the last)
+            const size_t cb = (size_t)(bh / p.Hk) * p.Sk;
+            i_start = max(i_start, __ldg(p.col_lo + cb + min(jt * 128, p.Sk - 1)) >> 7);
+            i_end = min(i_end, ((min(__ldg(p.col_hi + cb + min(jt * 128 + 127, p.Sk - 1)), p.Sq) - 1) >> 7) + 1);
+        }
+        n_it = max(i_end - i_start, 0) * p.G;
     };
     // consumer side of the scheduler broadcast: a whole warp calls it (lane 0 releases the slot), or one thread alone
     auto next_item = [&](uint32_t ix, bool solo = false) -> int {
@@ -214,19 +228,19 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     };
 
     if (warp == 11) {
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
     } else if (warp == 10) {
         // ------------------------------ statistics loader ------------------------------
         // Runs up to kStatStages tiles ahead of the math; the global loads of tile it+1 are in flight
         // while tile it waits for its slot, so their latency never reaches the critical path.
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         const int lane = lane_id();
         const uint32_t stat_addr = smem_u32(sStat);
         uint32_t gs = 0;
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
-            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
             // (q tile, row offset of the query head) walker over the item's iterations; with GQA it visits every head of the
             // group.  Lane l owns rows 4l..4l+3 of the tile: one 16-byte load each for LSE and delta (scalar, bounds-checked
             // loads only for a ragged last tile or an unaligned S_q) and one 16-byte shared store each.
@@ -236,7 +250,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             auto fetch = [&](float4& nl, float4& dl) {             // statistics of the walker's current tile, then advance
                 const int q0 = s_qtile * 128 + lane * 4;
                 const size_t off = s_row0 + q0;
-                if (++s_qtile == p.n_qtiles) { s_qtile = i_start; s_row0 += p.Sq; }
+                if (++s_qtile == i_end) { s_qtile = i_start; s_row0 += p.Sq; }
                 float l[4];
                 if (vec_ok && q0 + 4 <= p.Sq) {
                     const float4 lv = __ldg(reinterpret_cast<const float4*>(p.lse + off));
@@ -281,7 +295,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         }
     } else if (warp == 9) {
         // ----------------------------- TMA producer + scheduler -----------------------------
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         {   // whole warp, converged
             if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
             __syncwarp();
@@ -293,7 +307,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 sched_item[slot] = item;
                 mbar_arrive_e(&sched_full[slot]);
                 if (item >= n_items) break;
-                int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+                int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
                 mbar_wait(kv_free, (ix & 1) ^ 1, 442);        // K/V smem of the previous item released
                 if (n_it > 0) {
                     mbar_arrive_expect_tx_e(k_full, C::kTileBytes);
@@ -306,7 +320,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                         uint8_t* sQi = sStage + st * C::kStageBytes;
                         uint8_t* sdOi = sQi + C::kTileBytes;
                         const int q0 = l_qtile * 128, hcur = hq;
-                        if (++l_qtile == p.n_qtiles) { l_qtile = i_start; ++hq; }
+                        if (++l_qtile == i_end) { l_qtile = i_start; ++hq; }
                         mbar_wait(&stage_empty[st], ((git / C::kStages) & 1) ^ 1, 410);
                         mbar_arrive_expect_tx_e(&q_full[st], C::kTileBytes);
                         #pragma unroll
@@ -328,13 +342,13 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         }
     } else if (warp == 8) {
         // ---------------------------------- MMA issuer ----------------------------------
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aSt = smem_u32(sStage);
         uint32_t git = 0, gi = 0, nacc = 0;
         for (uint32_t ix = 0;; ++ix) {           // whole warp, converged
             const int item = next_item(ix);
             if (item >= n_items) break;
-            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
             auto qfull = [&](uint32_t g) { mbar_wait(&q_full[g % C::kStages], (g / C::kStages) & 1, 421); };
             auto dofull = [&](uint32_t g) { mbar_wait(&do_full[g % C::kStages], (g / C::kStages) & 1, 423); };
             auto stage_addr = [&](uint32_t g) { return aSt + (g % C::kStages) * C::kStageBytes; };
@@ -386,7 +400,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         }
     } else {
         // ------------------------------- compute warpgroups -------------------------------
-        reg_alloc<kBwdRegsCompute>();
+        reg_alloc<BwdRegs<D>::kCompute>();
         const int h = warp >> 2;                         // column half
         const int r = tid & 127;                         // kv row in tile == TMEM lane
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
@@ -399,15 +413,20 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
-            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
             const int kv_g = jt * 128 + r;
+            int q_lo = p.causal ? kv_g : 0, q_hi = p.Sq;  // queries that see my kv row
+            if (p.col_lo) {
+                const size_t ci = (size_t)(bh / p.Hk) * p.Sk + min(kv_g, p.Sk - 1);
+                q_lo = max(q_lo, __ldg(p.col_lo + ci)); q_hi = min(q_hi, __ldg(p.col_hi + ci));
+            }
             int qtile = i_start;                          // q tile of the current iteration (wraps per query head of the group)
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it;
                 const uint32_t ss = g % C::kStatStages;
                 const uint32_t stat = smem_u32(sStat) + ss * 1024 + h * 256;
                 const int q0 = qtile * 128 + h * 64;                 // global query index of my column 0
-                if (++qtile == p.n_qtiles) qtile = i_start;
+                if (++qtile == i_end) qtile = i_start;
                 mbar_wait(&stat_full[ss], (g / C::kStatStages) & 1, 430);
                 const uint32_t tSTi = tST + (kDoubleS ? (g & 1) * 128 : 0);
                 if (kDoubleS) mbar_wait((g & 1) ? s_full1 : s_full, (g >> 1) & 1, 431);
@@ -435,10 +454,10 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     }
                     if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
                 }
-                if (p.causal && q0 < kv_g) {                 // tile straddles the diagonal: keep q >= kv only
-                    const int cmin = kv_g - q0;
+                if (q0 < q_lo || q0 + 64 > q_hi) {           // tile straddles the diagonal / a range end: keep q_lo <= q < q_hi
+                    const int cmin = q_lo - q0, cmax = q_hi - 1 - q0;
                     #pragma unroll
-                    for (int c = 0; c < 64; ++c) if (c < cmin) pv[c] = 0.f;
+                    for (int c = 0; c < 64; ++c) if (c < cmin || c > cmax) pv[c] = 0.f;
                 }
                 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -576,10 +595,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDS = 256 + D;   // dS buffers: kColDS + 64*(g&1)
 
     // item -> (bh, q tile, number of kv tiles); descending q tile = heavy first under causal (:219 truncation)
-    auto decode = [&](int item, int& bh, int& iq, int& n_it) {
+    auto decode = [&](int item, int& bh, int& iq, int& jb, int& n_it) {
         int qt; item_to_head_tile(item, p.BH, p.n_qtiles, p.hc_dq, bh, qt);
         iq = p.n_qtiles - 1 - qt;
-        n_it = fwd_tile_iters(iq * 128, 0, p.Sq, p.Sk, p.causal);
+        n_it = fwd_item_iters(p.row_lo, p.row_hi, bh / p.H, iq * 128, 0, p.Sq, p.Sk, p.causal, jb);   // kv tiles jb .. jb + n_it - 1
     };
     auto next_item = [&](uint32_t ix) -> int {           // whole warp
         const uint32_t slot = ix & 1;
@@ -590,10 +609,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     };
 
     if (warp >= 10) {
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
     } else if (warp == 9) {
         // ----------------------------- TMA producer + scheduler (whole warp, converged) -----------------------------
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
         __syncwarp();
         uint32_t g = 0;
@@ -604,7 +623,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             sched_item[slot] = item;
             mbar_arrive_e(&sched_full[slot]);
             if (item >= n_items) break;
-            int bh, iq, n_it; decode(item, bh, iq, n_it);
+            int bh, iq, jb, n_it; decode(item, bh, iq, jb, n_it);
             mbar_wait(qdo_free, (ix & 1) ^ 1, 542);          // Q/dO smem of the previous item released
             mbar_arrive_expect_tx_e(q_full, C::kTileBytes);
             #pragma unroll
@@ -616,7 +635,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 mbar_wait(&k_empty[ks], ((g / C::kKStages) & 1) ^ 1, 510);
                 mbar_arrive_expect_tx_e(&k_full[ks], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sKj + c * 16384, &mapK, &k_full[ks], c * 64, it * 128, (bh % p.H) / p.G, bh / p.H);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sKj + c * 16384, &mapK, &k_full[ks], c * 64, (jb + it) * 128, (bh % p.H) / p.G, bh / p.H);
                 if (it == 0) {
                     mbar_arrive_expect_tx_e(do_full, C::kTileBytes);
                     #pragma unroll
@@ -625,20 +644,20 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 mbar_wait(&v_empty[vs], ((g / C::kVStages) & 1) ^ 1, 511);
                 mbar_arrive_expect_tx_e(&v_full[vs], C::kTileBytes);
                 #pragma unroll
-                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, it * 128, (bh % p.H) / p.G, bh / p.H);
+                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, (jb + it) * 128, (bh % p.H) / p.G, bh / p.H);
             }
             if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dq, 1u) + (int)gridDim.x : n_items;
             item = __shfl_sync(0xffffffffu, item, 0);
         }
     } else if (warp == 8) {
         // ---------------------------------- MMA issuer (whole warp, converged) ----------------------------------
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKr = smem_u32(sKr), aVr = smem_u32(sVr);
         uint32_t gi = 0;
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
-            int bh, iq, n_it; decode(item, bh, iq, n_it);
+            int bh, iq, jb, n_it; decode(item, bh, iq, jb, n_it);
             auto kfull = [&](uint32_t g) { mbar_wait(&k_full[g % C::kKStages], (g / C::kKStages) & 1, 521); };
             auto vfull = [&](uint32_t g) { mbar_wait(&v_full[g % C::kVStages], (g / C::kVStages) & 1, 523); };
             mbar_wait(q_full, ix & 1, 520);
@@ -670,7 +689,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             gi += n_it;
         }
     } else {
-        reg_alloc<kBwdRegsCompute>();
+        reg_alloc<BwdRegs<D>::kCompute>();
         const int h = warp >> 2;
         const int r = tid & 127;
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
@@ -684,13 +703,18 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
-            int bh, iq, n_it; decode(item, bh, iq, n_it);
+            int bh, iq, jb, n_it; decode(item, bh, iq, jb, n_it);
             const int row_g = iq * 128 + r;
             float nl = -INFINITY, dl = 0.f;
             if (row_g < p.Sq) {
                 const float l = __ldg(p.lse + (size_t)bh * p.Sq + row_g);
                 nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
                 dl = __ldg(p.delta + (size_t)bh * p.Sq + row_g);
+            }
+            int k_lo = 0, k_hi = p.Sk;                    // keys this row may see (before the causal clip)
+            if (p.row_lo) {
+                const size_t ri = (size_t)(bh / p.H) * p.Sq + min(row_g, p.Sq - 1);
+                k_lo = __ldg(p.row_lo + ri); k_hi = min(__ldg(p.row_hi + ri), p.Sk);
             }
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it;
@@ -718,12 +742,13 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     }
                     if (FA_BWD_STAGGER) named_bar_arrive(4 - h, 256);
                 }
-                const int k0 = it * 128 + h * 64;             // global key index of my column 0
-                int cmax = p.Sk - 1 - k0;
+                const int k0 = (jb + it) * 128 + h * 64;      // global key index of my column 0
+                int cmax = k_hi - 1 - k0;
                 if (p.causal) cmax = min(cmax, row_g - k0);
-                if (cmax < 63) {
+                const int cmin = k_lo - k0;
+                if (cmax < 63 || cmin > 0) {
                     #pragma unroll
-                    for (int c = 0; c < 64; ++c) if (c > cmax) pv[c] = 0.f;
+                    for (int c = 0; c < 64; ++c) if (c > cmax || c < cmin) pv[c] = 0.f;
                 }
                 mbar_wait(dp_full, g & 1, 531);
                 tc_fence_after();

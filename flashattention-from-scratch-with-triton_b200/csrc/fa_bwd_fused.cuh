@@ -163,7 +163,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     if (warp == 11) {
         // ------------------------------ dQ reducer ------------------------------
         // staged fp32 partial -> += into the accumulator [B*H, Sq, D] (rows past Sq are dropped by the tensor map)
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         uint32_t nd = 0;
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
@@ -190,7 +190,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         if (lane_id() == 0) tma_store_wait_all0();
     } else if (warp == 10) {
         // ------------------------------ statistics loader (as in the dK/dV kernel) ------------------------------
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         const int lane = lane_id();
         const uint32_t stat_addr = smem_u32(sStat);
         uint32_t gs = 0;
@@ -248,7 +248,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         }
     } else if (warp == 9) {
         // ----------------------------- TMA producer + scheduler (whole warp, converged) -----------------------------
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
         __syncwarp();
         uint32_t git = 0;
@@ -295,7 +295,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         }
     } else if (warp == 8) {
         // ---------------------------------- MMA issuer (whole warp, converged) ----------------------------------
-        reg_dealloc<kBwdRegsOther>();
+        reg_dealloc<BwdRegs<D>::kOther>();
         const uint32_t aKV = smem_u32(sKV), aSt = smem_u32(sStage), aDS = smem_u32(sDS);
         uint32_t git = 0, gi = 0;
         for (uint32_t ix = 0;; ++ix) {
@@ -350,7 +350,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         }
     } else {
         // ------------------------------- math warpgroups -------------------------------
-        reg_alloc<kBwdRegsCompute>();
+        reg_alloc<BwdRegs<D>::kCompute>();
         const int h = warp >> 2;                         // column half
         const int r = tid & 127;                         // kv row in tile == TMEM lane
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;

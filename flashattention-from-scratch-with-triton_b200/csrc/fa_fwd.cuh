@@ -31,6 +31,10 @@ struct FwdParams {
     float scale_log2;      // scale * log2(e)
     float* lse;            // [BH, Sq] fp32
     unsigned int* sched;   // work counter, zeroed before launch
+    // Optional per-row key ranges [B, Sq] (var-len packing, key padding, windows): query row i of batch b sees keys
+    // [row_lo, row_hi) (and, if causal, only keys <= i).  Both arrays must be non-decreasing in i.  NULL = [0, Sk).
+    const int* row_lo;
+    const int* row_hi;
 };
 
 template <int D> struct FwdCfg {
@@ -48,7 +52,12 @@ template <int D> struct FwdCfg {
 };
 
 constexpr int kFwdThreads = 384;    // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
-constexpr int kFwdRegsSoftmax = 208, kFwdRegsOther = 80;   // setmaxnreg split of the 168 x 384 launch pool
+// setmaxnreg split of the launch pool: the CTA owns 384 x 168 = 64512 registers, so 2 * softmax + other <= 504 per thread triple
+// (a split that needs more than the pool makes setmaxnreg.inc wait forever).
+// Measured: 216 / 72 at D=64 removes every spill but is 25-30 % SLOWER (the MMA / TMA warps' code degrades at 72), 208 / 88 at
+// D=128 changes nothing -> 208 / 80 everywhere.
+template <int D> struct FwdRegs { static constexpr int kSoftmax = 208, kOther = 80; };
+static_assert(2 * FwdRegs<64>::kSoftmax + FwdRegs<64>::kOther <= 504 && 2 * FwdRegs<128>::kSoftmax + FwdRegs<128>::kOther <= 504, "register pool");
 // Of every FA_FWD_POLY_DEN pairs of exponentials, FA_FWD_POLY_NUM are evaluated on the FMA pipe (ex2_poly2),
 // the rest on the MUFU unit: the exp loop is XU-saturated (profiles/), the polynomial shifts load to FFMA2.
 #ifndef FA_FWD_POLY_NUM
@@ -80,12 +89,31 @@ __device__ __forceinline__ int fwd_tile_iters(int q0, int t, int Sq, int Sk, int
     return min(n, nkv);
 }
 
-template <int D, bool kBf16>
+// Same with per-row key ranges: `jb` = first K/V tile of the item (from the range of the item's first row; ranges are
+// monotone, so it is the minimum), return = number of tiles from jb that tile `t` must visit (up to the range end of its last row).
+// Rows whose own range starts later / ends earlier are handled by the element mask.
+__device__ __forceinline__ int fwd_item_iters(const int* row_lo, const int* row_hi, int b, int q0, int t, int Sq, int Sk,
+                                              int causal, int& jb) {
+    if (!row_lo) { jb = 0; return fwd_tile_iters(q0, t, Sq, Sk, causal); }
+    jb = __ldg(row_lo + (size_t)b * Sq + min(q0, Sq - 1)) >> 7;
+    const int r0 = q0 + t * 128;
+    if (r0 >= Sq) return 0;
+    const int last_row = min(r0 + 127, Sq - 1);
+    int hi = min(__ldg(row_hi + (size_t)b * Sq + last_row), Sk);
+    if (causal) hi = min(hi, last_row + 1);
+    return max(((hi - 1) >> 7) - jb + 1, 0);
+}
+
+// kRanges: instantiation with the per-row key ranges (the plain operator keeps its register budget: the softmax loop sits at
+// the 208-register ceiling and three more live values spill)
+template <int D, bool kBf16, bool kRanges = false>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapO,
               const FwdParams p) {
     using C = FwdCfg<D>;
+    const int* const rlo = kRanges ? p.row_lo : nullptr;       // compile-time NULL in the plain instantiation
+    const int* const rhi = kRanges ? p.row_hi : nullptr;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem + C::kOffQ;
@@ -128,10 +156,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 11) {
-        reg_dealloc<kFwdRegsOther>();     // idle warp (register donor)
+        reg_dealloc<FwdRegs<D>::kOther>();     // idle warp (register donor)
     } else if (warp == 9) {
         // ================================ TMA producer + scheduler ================================
-        reg_dealloc<kFwdRegsOther>();
+        reg_dealloc<FwdRegs<D>::kOther>();
         {   // whole warp, converged; single-lane instructions elect their leader (fa_ptx.cuh)
             if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); }
             __syncwarp();
@@ -146,8 +174,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 if (item >= p.n_items) break;
                 int bh, qt; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh, qt);
                 const int q0 = (p.n_qblk - 1 - qt) * 256;                   // heavy (late) query blocks first
-                const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
-                const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
+                int jb;
+                const int n0 = fwd_item_iters(rlo, rhi, bh / p.H, q0, 0, p.Sq, p.Sk, p.causal, jb);
+                const int n1 = fwd_item_iters(rlo, rhi, bh / p.H, q0, 1, p.Sq, p.Sk, p.causal, jb);
                 const int n = max(n0, n1);
                 auto load_q = [&](int t, uint32_t& cnt) {
                     mbar_wait(&q_empty[t], (cnt & 1) ^ 1, 101 + t);
@@ -163,7 +192,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     mbar_arrive_expect_tx_e(&kv_full[st], C::kTileBytes);
                     #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c)
-                        tma_load_4d_e(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, j * 128, (bh % p.H) / p.G, bh / p.H);
+                        tma_load_4d_e(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, (jb + j) * 128, (bh % p.H) / p.G, bh / p.H);
                     ++kv_cnt;
                 };
                 if (n0 > 0) load_q(0, q_cnt0);
@@ -180,7 +209,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         // One issuing thread PER Q tile (warp 8 -> tile 0, warp 10 -> tile 1).  The two tiles' MMA chains
         // are independent (own TMEM regions, read-only K/V), so neither tile ever waits behind a barrier
         // that belongs to the other.  Each K/V ring slot is released by both threads (kv_empty count 2).
-        reg_dealloc<kFwdRegsOther>();
+        reg_dealloc<FwdRegs<D>::kOther>();
         if constexpr (C::kSepP) {
         {   // whole warp, converged
             const int t = (warp == 8) ? 0 : 1;
@@ -214,10 +243,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const int item = __shfl_sync(0xffffffffu, sched_item[slot], 0);   // warp-uniform for the compiler
                 mbar_arrive_e(&sched_empty[slot]);
                 if (item >= p.n_items) break;
-                int bh_, qt; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh_, qt);
+                int bh_, qt, jb_; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh_, qt);
                 const int q0 = (p.n_qblk - 1 - qt) * 256;
-                const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
-                const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
+                const int n0 = fwd_item_iters(rlo, rhi, bh_ / p.H, q0, 0, p.Sq, p.Sk, p.causal, jb_);
+                const int n1 = fwd_item_iters(rlo, rhi, bh_ / p.H, q0, 1, p.Sq, p.Sk, p.causal, jb_);
                 const int n = max(n0, n1), nt = t ? n1 : n0;
                 // ring elements of this item: K(j) = kv_cnt + 2j, V(j) = kv_cnt + 2j + 1
                 auto do_s = [&](int j) {                   // consume K(j): S_t(j) if this tile needs it
@@ -298,10 +327,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const int item = __shfl_sync(0xffffffffu, sched_item[slot], 0);   // warp-uniform for the compiler
                 mbar_arrive_e(&sched_empty[slot]);
                 if (item >= p.n_items) break;
-                int bh_, qt; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh_, qt);
+                int bh_, qt, jb_; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh_, qt);
                 const int q0 = (p.n_qblk - 1 - qt) * 256;
-                const int n0 = fwd_tile_iters(q0, 0, p.Sq, p.Sk, p.causal);
-                const int n1 = fwd_tile_iters(q0, 1, p.Sq, p.Sk, p.causal);
+                const int n0 = fwd_item_iters(rlo, rhi, bh_ / p.H, q0, 0, p.Sq, p.Sk, p.causal, jb_);
+                const int n1 = fwd_item_iters(rlo, rhi, bh_ / p.H, q0, 1, p.Sq, p.Sk, p.causal, jb_);
                 const int n = max(n0, n1);
                 // ---- S_t(0)
                 {
@@ -359,7 +388,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
     } else {
         // ================================= softmax warpgroups (0,1) ================================
-        reg_alloc<kFwdRegsSoftmax>();
+        reg_alloc<FwdRegs<D>::kSoftmax>();
         const int t = warp >> 2;                       // Q tile handled by this warpgroup
         const int r = tid & 127;                       // row inside the tile == TMEM lane
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
@@ -379,13 +408,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             if (item >= p.n_items) break;
             int bh, qt; item_to_head_tile(item, p.BH, p.n_qblk, p.hc, bh, qt);
             const int q0 = (p.n_qblk - 1 - qt) * 256;
-            const int nt = fwd_tile_iters(q0, t, p.Sq, p.Sk, p.causal);
-            const int n_rounds = max(nt, fwd_tile_iters(q0, 1 - t, p.Sq, p.Sk, p.causal));
+            int jb;
+            const int nt = fwd_item_iters(rlo, rhi, bh / p.H, q0, t, p.Sq, p.Sk, p.causal, jb);
+            const int n_rounds = max(nt, fwd_item_iters(rlo, rhi, bh / p.H, q0, 1 - t, p.Sq, p.Sk, p.causal, jb));
             if (nt == 0) {
                 if (FA_FWD_STAGGER) for (int j = 0; j < n_rounds; ++j) { named_bar_sync(3 + t, 256); named_bar_arrive(4 - t, 256); }
                 continue;
             }
             const int row_g = q0 + t * 128 + r;
+            int k_lo = 0, k_hi = p.Sk;                    // keys this row may see (before the causal clip)
+            if constexpr (kRanges) {
+                const size_t ri = (size_t)(bh / p.H) * p.Sq + min(row_g, p.Sq - 1);
+                k_lo = __ldg(p.row_lo + ri); k_hi = min(__ldg(p.row_hi + ri), p.Sk);
+            }
             float m = -INFINITY, l = 0.f;
             for (int j = 0; j < nt; ++j) {
                 mbar_wait(&s_full[t], ph_s, 301); ph_s ^= 1;
@@ -396,14 +431,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 tc_wait_ld();
                 if constexpr (C::kSepP) { tc_fence_before(); mbar_arrive(&s_empty[t]); }   // S_t(j+1) may overwrite S_t now
                 // element mask only on tiles that straddle the diagonal or the end of K
-                int cmax = p.Sk - 1 - j * 128;                              // last valid column in this tile
-                if (p.causal) cmax = min(cmax, row_g - j * 128);
-                if (cmax < 127) {
+                const int kbase = (kRanges ? jb + j : j) * 128;
+                int cmax = (kRanges ? k_hi : p.Sk) - 1 - kbase;             // last valid column in this tile
+                if (p.causal) cmax = min(cmax, row_g - kbase);
+                const int cmin = kRanges ? k_lo - kbase : 0;                // first valid column (> 0 only with row ranges)
+                if (cmax < 127 || cmin > 0) {
                     #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         #pragma unroll
                         for (int i = 0; i < 32; ++i)
-                            if (q * 32 + i > cmax) s[q][i] = 0xff800000u;  // -inf
+                            if (q * 32 + i > cmax || q * 32 + i < cmin) s[q][i] = 0xff800000u;  // -inf
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
                 #pragma unroll
@@ -421,7 +458,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     // lazy rescale (warp-uniform decision: tcgen05.ld/st are warp-collective)
                     const bool need = (m_new - m) * c2 > kLazyRescaleLog2;
                     if (__any_sync(0xffffffffu, need)) {
-                        const float corr = ex2_approx((m - m_new) * c2);     // m = -inf -> 0
+                        // m = -inf -> 0.  A row that is STILL fully masked (range masks: its keys start tiles later) is rescaled with
+                        // its warp (the decision is warp-uniform): -inf - -inf would poison l and O with NaN
+                        const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx((m - m_new) * c2);
                         l *= corr;
                         #pragma unroll
                         for (int q = 0; q < D / 32; ++q) {

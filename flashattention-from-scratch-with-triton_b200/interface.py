@@ -51,7 +51,55 @@ def _strides(*tensors):
     return arr
 
 
-def flash_attention_forward(Q, K, V, is_causal, sm_scale=None):
+class Ranges:
+    """Range mask on top of (or instead of) causal: query row i of batch b sees keys [row_lo[b,i], row_hi[b,i]); the same mask seen
+    from the key side is col_lo / col_hi [B, S_k].  int32 CUDA tensors, non-decreasing along the sequence.  Tiles outside the
+    ranges are skipped by the kernels (include/fa_sm100.h, fa_sm100_*_ranges)."""
+
+    def __init__(self, row_lo, row_hi, col_lo, col_hi):
+        self.row_lo, self.row_hi, self.col_lo, self.col_hi = (t.to(torch.int32).contiguous() for t in (row_lo, row_hi, col_lo, col_hi))
+
+    @staticmethod
+    def from_cu_seqlens(cu_seqlens, total=None, device=None):
+        """Packed self-attention (Phase_6.md:160-174): tokens [cu[s], cu[s+1]) form sequence s and attend only inside it."""
+        cu = torch.as_tensor(cu_seqlens, dtype=torch.int64, device=device)
+        total = int(cu[-1]) if total is None else total
+        pos = torch.arange(total, device=cu.device)
+        sid = torch.searchsorted(cu[1:].contiguous(), pos, right=True).clamp_(max=cu.numel() - 2)
+        lo, hi = cu[sid][None], cu[sid + 1][None]
+        return Ranges(lo, hi, lo, hi)
+
+    @staticmethod
+    def from_key_padding(seqlens_k, S_q, S_k, device=None):
+        """Padded batch: batch b has seqlens_k[b] valid keys (>= 1); padded keys receive zero gradient."""
+        n = torch.as_tensor(seqlens_k, dtype=torch.int64, device=device)
+        B = n.numel()
+        row_lo = torch.zeros(B, S_q, dtype=torch.int64, device=n.device)
+        row_hi = n[:, None].expand(B, S_q)
+        valid = torch.arange(S_k, device=n.device)[None, :] < n[:, None]
+        col_lo = torch.where(valid, 0, S_q)
+        col_hi = torch.full((B, S_k), S_q, dtype=torch.int64, device=n.device)
+        return Ranges(row_lo, row_hi, col_lo, col_hi)
+
+    @staticmethod
+    def sliding_window(B, S, window, device=None):
+        """Causal sliding window: query i sees keys (i - window, i].  Use with is_causal=True."""
+        i = torch.arange(S, device=device)
+        row_lo = (i - window + 1).clamp_(min=0)[None].expand(B, S)
+        row_hi = torch.full((B, S), S, dtype=torch.int64, device=device)
+        col_lo = i[None].expand(B, S)
+        col_hi = (i + window).clamp_(max=S)[None].expand(B, S)
+        return Ranges(row_lo, row_hi, col_lo, col_hi)
+
+    def row_ranges(self):
+        return self.row_lo, self.row_hi
+
+
+def _rp(t):
+    return t.data_ptr() if t is not None else None
+
+
+def flash_attention_forward(Q, K, V, is_causal, sm_scale=None, ranges=None):
     """Allocate O / LSE and launch the forward kernel (reference :14-60).
 
     Q: [B,H,S_q,D], K,V: [B,H,S_k,D] CUDA fp16/bf16, contiguous or TMA-compatible strided views.  Returns
@@ -66,28 +114,36 @@ def flash_attention_forward(Q, K, V, is_causal, sm_scale=None):
     LSE = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
     st = _strides(Q, K, V, O)
     with torch.cuda.device(Q.device):
-        rc = lib.fa_sm100_fwd_strided(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), LSE.data_ptr(),
-                                      B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
-                                      float(sm_scale) if sm_scale is not None else 0.0, st, _stream(Q))
-    _cabi.check("fa_sm100_fwd_strided", rc)
+        if ranges is not None:
+            assert ranges.row_lo.shape == (B, S_q) and ranges.row_hi.shape == (B, S_q) and ranges.row_lo.device == Q.device
+        rc = lib.fa_sm100_fwd_ranges(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), LSE.data_ptr(),
+                                     B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                     float(sm_scale) if sm_scale is not None else 0.0, st,
+                                     _rp(ranges.row_lo if ranges else None), _rp(ranges.row_hi if ranges else None), _stream(Q))
+    _cabi.check("fa_sm100_fwd_ranges", rc)
     return O, LSE
 
 
 BWD_DELTA, BWD_DQ, BWD_DKV = 1, 2, 4
 
 
-def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, parts, sm_scale=None):
+def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, parts, sm_scale=None, ranges=None):
     """Launch a subset of the backward kernels into caller-provided outputs (per-kernel timing, ring hops)."""
     lib = _cabi.load()
     B, H, S_q, D = Q.shape
     S_k = K.shape[2]
     st = _strides(Q, K, V, O, dO, dQ, dK, dV)
     with torch.cuda.device(Q.device):
-        rc = lib.fa_sm100_bwd_strided(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
-                                      LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
-                                      B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
-                                      float(sm_scale) if sm_scale is not None else 0.0, st, _stream(Q), int(parts))
-    _cabi.check("fa_sm100_bwd_strided", rc)
+        if ranges is not None:
+            assert ranges.col_lo.shape == (B, S_k) and ranges.col_hi.shape == (B, S_k) and ranges.row_lo.shape == (B, S_q)
+        r = ranges
+        rc = lib.fa_sm100_bwd_ranges(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
+                                     LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
+                                     B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                     float(sm_scale) if sm_scale is not None else 0.0, st,
+                                     _rp(r.row_lo if r else None), _rp(r.row_hi if r else None), _rp(r.col_lo if r else None),
+                                     _rp(r.col_hi if r else None), _stream(Q), int(parts))
+    _cabi.check("fa_sm100_bwd_ranges", rc)
 
 
 # Backward algorithm.  Head dim 64 defaults to the fused single-pass kernel (5 GEMMs and one exponential per score
@@ -137,15 +193,16 @@ def _empty_like_kernel(t):
     return e if tma_compatible(e) else torch.empty(t.shape, dtype=t.dtype, device=t.device)
 
 
-def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None):
+def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None, ranges=None):
     """Allocate dQ / dK / dV (+ fp32 delta) and launch the backward kernels (reference :62-128)."""
     B, H, S_q, D = Q.shape
     dQ, dK, dV = _empty_like_kernel(Q), _empty_like_kernel(K), _empty_like_kernel(V)      # reference :71-73
     delta = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
-    if fused_backward_supported(Q) and not _deterministic:
+    if fused_backward_supported(Q) and not _deterministic and ranges is None:
         flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale)
-    else:
-        flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, BWD_DELTA | BWD_DQ | BWD_DKV, sm_scale)
+    else:                                                  # range masks run on the two-kernel path
+        flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, BWD_DELTA | BWD_DQ | BWD_DKV, sm_scale,
+                                       ranges)
     return dQ, dK, dV
 
 
@@ -153,7 +210,7 @@ class FlashAttentionFunction(torch.autograd.Function):
     """Same contract as the reference class (reference :130-166)."""
 
     @staticmethod
-    def forward(ctx, Q, K, V, is_causal: bool, sm_scale=None):
+    def forward(ctx, Q, K, V, is_causal: bool, sm_scale=None, ranges=None):
         assert Q.is_cuda and K.is_cuda and V.is_cuda                       # :133
         assert Q.dtype in (torch.float16, torch.bfloat16)                  # :134
         assert Q.shape[-1] == K.shape[-1] == V.shape[-1]                   # :135
@@ -161,23 +218,37 @@ class FlashAttentionFunction(torch.autograd.Function):
         assert K.dtype == Q.dtype and V.dtype == Q.dtype
         assert K.shape[:3] == V.shape[:3] and K.shape[0] == Q.shape[0] and Q.shape[1] % K.shape[1] == 0   # GQA/MQA: Hk | H
         Q_ = as_kernel_layout(Q); K_ = as_kernel_layout(K); V_ = as_kernel_layout(V)   # :138-140, without needless copies
-        O, LSE = flash_attention_forward(Q_, K_, V_, is_causal, sm_scale)
+        O, LSE = flash_attention_forward(Q_, K_, V_, is_causal, sm_scale, ranges)
         ctx.save_for_backward(Q_, K_, V_, O, LSE)                          # :145 (same set, same order)
         ctx.is_causal = is_causal                                          # :147
         ctx.sm_scale = sm_scale
+        ctx.ranges = ranges
         return O
 
     @staticmethod
     def backward(ctx, dO):
         Q, K, V, O, LSE = ctx.saved_tensors                                # :154
         dO_ = as_kernel_layout(dO)                                         # :156
-        dQ, dK, dV = flash_attention_backward(Q, K, V, O, dO_, LSE, ctx.is_causal, ctx.sm_scale)
-        return dQ, dK, dV, None, None                                      # :166 (+None for sm_scale)
+        dQ, dK, dV = flash_attention_backward(Q, K, V, O, dO_, LSE, ctx.is_causal, ctx.sm_scale, ctx.ranges)
+        return dQ, dK, dV, None, None, None                                # :166 (+None for sm_scale, ranges)
 
 
-def flash_attention(Q, K, V, is_causal=False, *, sm_scale=None):
-    """O = softmax(Q K^T * scale [+ causal mask]) V, differentiable w.r.t. Q, K, V (reference :169-170)."""
-    return FlashAttentionFunction.apply(Q, K, V, is_causal, sm_scale)
+def flash_attention(Q, K, V, is_causal=False, *, sm_scale=None, ranges=None):
+    """O = softmax(Q K^T * scale [+ causal mask]) V, differentiable w.r.t. Q, K, V (reference :169-170).
+    ``ranges`` (a Ranges object) adds a per-row key-range mask: packed sequences, key padding, sliding windows."""
+    return FlashAttentionFunction.apply(Q, K, V, is_causal, sm_scale, ranges)
+
+
+def flash_attention_varlen(q, k, v, cu_seqlens, is_causal=False, *, sm_scale=None):
+    """Variable-length self-attention over PACKED sequences (the tutorial's own next step, Phase_6.md:160-174):
+    q [total, H, D], k / v [total, Hk, D]; tokens cu_seqlens[s] .. cu_seqlens[s+1]-1 form sequence s.  Zero-copy: the packed
+    buffers are addressed as one batch of length `total` through strided tensor maps, the block-diagonal mask is a Ranges
+    object and the kernels skip every tile that lies outside a sequence.  Returns O [total, H, D]."""
+    total = q.shape[0]
+    ranges = Ranges.from_cu_seqlens(cu_seqlens, total, device=q.device)
+    O = flash_attention(q.transpose(0, 1)[None], k.transpose(0, 1)[None], v.transpose(0, 1)[None], is_causal,
+                        sm_scale=sm_scale, ranges=ranges)
+    return O[0].transpose(0, 1)
 
 
 attention = flash_attention

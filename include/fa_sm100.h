@@ -72,6 +72,23 @@ int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void
                          float sm_scale, const long long* strides, void* stream, int parts);
 #define FA_ERR_STRIDE (-8)    /* a stride is not a multiple of 8 elements or is negative */
 
+/* Range-masked variants (variable-length / packed sequences, key padding, windows; the reference has no masks
+ * besides causal, Phase_6.md:160-174 describes cu_seqlens packing as future work).  Query row i of batch b attends to keys
+ * [row_lo[b*Sq+i], row_hi[b*Sq+i]) — intersected with keys <= i when `causal` — and the same mask seen from the key side is
+ * col_lo/col_hi [B,Sk]: key row j is seen by queries [col_lo[b*Sk+j], col_hi[b*Sk+j]).  All four are device int32 arrays,
+ * non-decreasing along the sequence (the kernels derive their tile ranges from the first and last row of a tile), and must
+ * describe the same mask; every query row must see at least one key.  Tiles outside the ranges are skipped, not masked:
+ * packing N sequences costs the sum of their squares.  Packed [total,H,D] tensors are passed as B = 1, Sq = Sk = total with
+ * strides {0, D, H*D}.  NULL ranges = the plain operator.  The backward is the deterministic two-kernel path. */
+int fa_sm100_fwd_ranges(const void* q, const void* k, const void* v, void* o, float* lse,
+                        int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                        const long long* strides, const int* row_lo, const int* row_hi, void* stream);
+int fa_sm100_bwd_ranges(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                        const float* lse, void* dq, void* dk, void* dv, float* delta,
+                        int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                        const long long* strides, const int* row_lo, const int* row_hi,
+                        const int* col_lo, const int* col_hi, void* stream, int parts);
+
 /* Same as fa_sm100_bwd but launches only the selected kernels: parts is a bit mask of
  * FA_BWD_DELTA (1), FA_BWD_DQ (2), FA_BWD_DKV (4).  dQ and dKV read `delta`, so it must have been
  * produced already when FA_BWD_DELTA is not set.  Used to time each kernel on its own (bench.py). */

@@ -159,7 +159,7 @@ def backward_blocked(Q, K, V, O, dO, LSE, is_causal, BLOCK_M=64, BLOCK_N=64, sm_
 
 
 def closed_form(Q, K, V, dO=None, is_causal: bool = False, sm_scale: Optional[float] = None,
-                dtype: torch.dtype = torch.float64, q_offset: int = 0, k_offset: int = 0):
+                dtype: torch.dtype = torch.float64, q_offset: int = 0, k_offset: int = 0, row_ranges=None):
     """Exact (materialised-scores) attention in ``dtype`` — no tiling, no 16-bit rounding.
 
     Forward: Phase_3.md:699-708 (LSE = logsumexp of masked, scaled scores).
@@ -167,6 +167,8 @@ def closed_form(Q, K, V, dO=None, is_causal: bool = False, sm_scale: Optional[fl
     dS = P∘(dP−delta), dQ = dS K·scale, dK = dSᵀ Q·scale.
     ``q_offset``/``k_offset`` shift the global row/col indices used by the causal mask
     (ring hops).  Fully-masked rows give O = 0, LSE = −inf.
+    ``row_ranges`` = (lo, hi), int tensors [B, S_q]: query row i additionally sees only keys lo[b,i] <= j < hi[b,i]
+    (packed variable-length sequences as in Phase_6.md:160-174, key padding, sliding windows).
     """
     D = Q.shape[-1]
     scale = 1.0 / math.sqrt(D) if sm_scale is None else sm_scale
@@ -176,6 +178,11 @@ def closed_form(Q, K, V, dO=None, is_causal: bool = False, sm_scale: Optional[fl
         rows = torch.arange(Q.shape[2]) + q_offset
         cols = torch.arange(K.shape[2]) + k_offset
         S = S.masked_fill(~(rows[:, None] >= cols[None, :]), float("-inf"))
+    if row_ranges is not None:
+        lo, hi = (t.to(torch.int64).cpu() for t in row_ranges)
+        cols = torch.arange(K.shape[2])
+        keep = (cols[None, None, :] >= lo[:, :, None]) & (cols[None, None, :] < hi[:, :, None])      # [B, S_q, S_k]
+        S = S.masked_fill(~keep[:, None], float("-inf"))
     LSE = torch.logsumexp(S, dim=-1)
     P = torch.exp(S - LSE[..., None])
     P = torch.nan_to_num(P, nan=0.0)           # fully masked rows: exp(-inf - -inf)

@@ -62,6 +62,9 @@ def test_argument_validation_without_gpu(lib):
     assert fused(acc=None) == -1
     assert lib.fa_sm100_bwd_fused_workspace(2, 4, 256, 64) == 2 * 4 * 256 * 64 * 4
     assert lib.fa_sm100_bwd_fused_workspace(2, 4, 256, 128) == 0
+    # range masks: lo / hi arrays come in pairs (quadruples for the backward)
+    assert lib.fa_sm100_fwd_ranges(p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, None, p, None, None) == -1
+    assert lib.fa_sm100_bwd_ranges(p, p, p, p, p, p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, None, p, p, p, None, None, 7) == -1
     assert lib.fa_sm100_delta(p, None, p, 1, 1, 128, 64, 1, None) == -1
     assert lib.fa_sm100_merge(p, p, p, None, 1, 1, 128, 64, 1, 128, 0, None) == -1
     assert lib.fa_sm100_merge(p, p, p, p, 1, 1, 128, 64, 1, 128, 64, None) == -4

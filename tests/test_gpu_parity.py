@@ -375,3 +375,66 @@ def test_gqa_mqa_head_sharing(H, Hk, D, causal):
     q2 = Q.cuda().requires_grad_(True)
     fa.flash_attention(q2, k2, v2, causal).backward(dO.cuda())
     assert torch.equal(k2.grad, k.grad) and torch.equal(v2.grad, v.grad)      # deterministic
+
+
+def _check_ranges(Q, K, V, dO, causal, ranges, tol_kv=1e-2):
+    """CUDA path with a Ranges mask against the fp64 closed form with the same mask (dense, on the CPU)."""
+    q, k, v = (t.cuda().requires_grad_(True) for t in (Q, K, V))
+    O = fa.flash_attention(q, k, v, causal, ranges=ranges)
+    O.backward(dO.cuda())
+    _, LSE = fa.flash_attention_forward(q.detach(), k.detach(), v.detach(), causal, ranges=ranges)
+    G = Q.shape[1] // K.shape[1]
+    rO, rLSE, rdQ, rdKe, rdVe = orc.closed_form(Q, K.repeat_interleave(G, dim=1), V.repeat_interleave(G, dim=1), dO, causal,
+                                                row_ranges=(ranges.row_lo.cpu(), ranges.row_hi.cpu()))
+    B, Hk, Sk, D = K.shape
+    rdK = rdKe.reshape(B, Hk, G, Sk, D).sum(2); rdV = rdVe.reshape(B, Hk, G, Sk, D).sum(2)
+    assert (LSE.cpu() - rLSE.float()).abs().max() < LSE_TOL
+    for name, x, r, tol in (("O", O, rO, 1e-2), ("dQ", q.grad, rdQ, 1e-2), ("dK", k.grad, rdK, tol_kv), ("dV", v.grad, rdV, tol_kv)):
+        x = x.detach().cpu()
+        assert torch.isfinite(x.float()).all(), name
+        assert _close(x, r, tol, tol), (name, (x.float() - r.float()).abs().max().item())
+    import flashattn_b200._cabi as cabi
+    assert cabi.last_hang() is None
+    return O.detach()
+
+
+@pytest.mark.parametrize("causal", [False, True], ids=["full", "causal"])
+@pytest.mark.parametrize("D,H,Hk", [(64, 4, 4), (128, 4, 2)], ids=["d64", "d128gqa"])
+def test_varlen_packed_sequences(D, H, Hk, causal):
+    """Packed variable-length self-attention (cu_seqlens; Phase_6.md:160-174 lists it as future work): block-diagonal mask
+    through Ranges, zero-copy [total, H, D] layout, tiles outside a sequence skipped.  Sequence boundaries fall inside tiles,
+    on tile edges and inside one 256-row forward item."""
+    lens = [100, 333, 27, 512, 128, 1, 250]
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    total = cu[-1]
+    g = torch.Generator().manual_seed(31)
+    q = torch.randn(total, H, D, generator=g).bfloat16(); do = torch.randn(total, H, D, generator=g).bfloat16()
+    k = torch.randn(total, Hk, D, generator=g).bfloat16(); v = torch.randn(total, Hk, D, generator=g).bfloat16()
+    ranges = fa.Ranges.from_cu_seqlens(cu, total, device="cuda")
+    to4 = lambda t: t.transpose(0, 1)[None]
+    O = _check_ranges(to4(q), to4(k), to4(v), to4(do), causal, ranges, tol_kv=2e-2 if H != Hk else 1e-2)
+    # the packed entry point returns the same thing in the packed layout
+    Op = fa.flash_attention_varlen(q.cuda(), k.cuda(), v.cuda(), torch.tensor(cu), causal)
+    assert Op.shape == (total, H, D) and torch.equal(Op, O[0].transpose(0, 1))
+    # and every sequence equals the plain operator run on that sequence alone (up to tile-alignment rounding)
+    for s in (1, 3):
+        sl = slice(cu[s], cu[s + 1])
+        Os = fa.flash_attention(to4(q[sl]).cuda().contiguous(), to4(k[sl]).cuda().contiguous(), to4(v[sl]).cuda().contiguous(), causal)
+        assert _close(Os[0].transpose(0, 1), Op[sl], 4e-3, 4e-3)
+
+
+@pytest.mark.parametrize("D", [64, 128])
+def test_key_padding_and_sliding_window(D):
+    g = torch.Generator().manual_seed(33)
+    B, H, S = 2, 3, 640
+    Q, K, V, dO = (torch.randn(B, H, S, D, generator=g).bfloat16() for _ in range(4))
+    # key padding: batch 0 has 200 valid keys, batch 1 all of them; padded keys get exactly zero gradient
+    r = fa.Ranges.from_key_padding([200, S], S, S, device="cuda")
+    _check_ranges(Q, K, V, dO, False, r)
+    k = K.cuda().requires_grad_(True); v = V.cuda().requires_grad_(True)
+    fa.flash_attention(Q.cuda(), k, v, False, ranges=r).backward(dO.cuda())
+    assert (k.grad[0, :, 200:] == 0).all() and (v.grad[0, :, 200:] == 0).all()
+    # causal sliding window of 200 keys: only ~1/3 of the causal tiles are visited
+    _check_ranges(Q, K, V, dO, True, fa.Ranges.sliding_window(B, S, 200, device="cuda"))

@@ -87,3 +87,30 @@ def test_merge_partials_is_attention_over_union(causal):
     ninf = torch.full_like(La.float(), float("-inf"))
     Oi, Li = orc.merge_partials(torch.zeros_like(Oa).float(), ninf, Oa.float(), La.float())
     assert torch.equal(Li, La.float()) and (Oi - Oa.float()).abs().max() < 1e-6
+
+
+def test_range_mask_oracle_and_helpers():
+    """closed_form(row_ranges=...) equals per-sequence attention for a packed batch, and the Ranges helpers are consistent:
+    the key-side ranges describe the same mask as the query-side ranges."""
+    import flashattn_b200 as fa
+    cu = [0, 5, 12, 13, 20]
+    total, H, D = cu[-1], 2, 16
+    g = torch.Generator().manual_seed(3)
+    Q, K, V, dO = (torch.randn(1, H, total, D, generator=g) for _ in range(4))
+    r = fa.Ranges.from_cu_seqlens(cu, total)
+    for causal in (False, True):
+        O, LSE, dQ, dK, dV = orc.closed_form(Q, K, V, dO, causal, row_ranges=r.row_ranges())
+        for s in range(len(cu) - 1):
+            sl = slice(cu[s], cu[s + 1])
+            o, lse, dq, dk, dv = orc.closed_form(Q[:, :, sl], K[:, :, sl], V[:, :, sl], dO[:, :, sl], causal)
+            for a, b in ((O[:, :, sl], o), (LSE[:, :, sl], lse), (dQ[:, :, sl], dq), (dK[:, :, sl], dk), (dV[:, :, sl], dv)):
+                assert (a - b).abs().max() < 1e-10
+    for rr, Sq, Sk in ((r, total, total), (fa.Ranges.from_key_padding([3, 7], 6, 7), 6, 7), (fa.Ranges.sliding_window(2, 9, 4), 9, 9)):
+        i = torch.arange(Sq)[None, :, None]; j = torch.arange(Sk)[None, None, :]
+        from_rows = (j >= rr.row_lo[:, :, None]) & (j < rr.row_hi[:, :, None])
+        from_cols = (i >= rr.col_lo[:, None, :]) & (i < rr.col_hi[:, None, :])
+        if rr is not r and Sq == 9:                       # the window helper is meant to be combined with the causal mask
+            from_rows &= (i >= j); from_cols &= (i >= j)
+        assert torch.equal(from_rows, from_cols)
+        for t in (rr.row_lo, rr.row_hi, rr.col_lo, rr.col_hi):
+            assert (t[:, 1:] >= t[:, :-1]).all()         # monotone: the kernels take tile ranges from first / last rows
