@@ -86,6 +86,23 @@ def build_bringup(force: bool = False) -> str:
     return BRINGUP
 
 
+MICROBENCH = os.path.join(ROOT, "build", "fa_microbench")
+
+
+def build_microbench(force: bool = False) -> str:
+    """build/fa_microbench: tcgen05.ld / MUFU throughput probes (profiles/r01_microbench_tmem_mufu.txt)."""
+    os.makedirs(os.path.dirname(MICROBENCH), exist_ok=True)
+    srcs = [os.path.join(CSRC, "fa_microbench.cu"), os.path.join(CSRC, "fa_ptx.cuh")]
+    if not force and not _stale(MICROBENCH, srcs):
+        return MICROBENCH
+    cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-o", MICROBENCH, srcs[0]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building fa_microbench")
+    return MICROBENCH
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
@@ -99,3 +116,4 @@ if __name__ == "__main__":
     print(build_lib(a.force, a.verbose))
     if a.bringup:
         print(build_bringup(a.force))
+        print(build_microbench(a.force))

@@ -14,6 +14,7 @@ alias ``attention`` (BASELINE.json's spelling).
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -27,10 +28,31 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class _on_device:
+    """torch.cuda.device(d) as a context only when d is not already current: the context manager costs ~10 us per call,
+    comparable to the whole launch path, and a short step (C2: 0.2 ms on the GPU) must not become host-bound."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, t: torch.Tensor):
+        self.ctx = None if t.device.index == torch.cuda.current_device() else torch.cuda.device(t.device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 def tma_compatible(t: torch.Tensor) -> bool:
     """True if a [B,H,S,D] tensor can be addressed by the kernels' 4-D tensor maps as it is: D contiguous,
     every other stride a multiple of 8 elements (16 bytes) for dims of extent > 1, 16-byte aligned base."""
-    if t.ndim != 4 or t.stride(3) != 1 or t.data_ptr() % 16:
+    if t.ndim != 4 or t.data_ptr() % 16:
+        return False
+    if t.is_contiguous():                                  # fast path: D is a multiple of 8 for every supported head dim
+        return t.shape[3] % 8 == 0
+    if t.stride(3) != 1:
         return False
     return all(t.shape[i] == 1 or (t.stride(i) > 0 and t.stride(i) % 8 == 0) for i in range(3)) and \
         (t.shape[2] == 1 or t.stride(2) >= t.shape[3])
@@ -44,7 +66,8 @@ def as_kernel_layout(t: torch.Tensor) -> torch.Tensor:
 
 
 def _strides(*tensors):
-    import ctypes
+    if all(t.is_contiguous() for t in tensors):
+        return None                                        # NULL = all contiguous [B,H,S,D] (include/fa_sm100.h)
     arr = (ctypes.c_longlong * (3 * len(tensors)))()
     for i, t in enumerate(tensors):
         arr[3 * i], arr[3 * i + 1], arr[3 * i + 2] = t.stride(0), t.stride(1), t.stride(2)
@@ -113,7 +136,7 @@ def flash_attention_forward(Q, K, V, is_causal, sm_scale=None, ranges=None):
         O = torch.empty((B, H, S_q, D), dtype=Q.dtype, device=Q.device)
     LSE = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
     st = _strides(Q, K, V, O)
-    with torch.cuda.device(Q.device):
+    with _on_device(Q):
         if ranges is not None:
             assert ranges.row_lo.shape == (B, S_q) and ranges.row_hi.shape == (B, S_q) and ranges.row_lo.device == Q.device
         rc = lib.fa_sm100_fwd_ranges(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), LSE.data_ptr(),
@@ -133,7 +156,7 @@ def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_ca
     B, H, S_q, D = Q.shape
     S_k = K.shape[2]
     st = _strides(Q, K, V, O, dO, dQ, dK, dV)
-    with torch.cuda.device(Q.device):
+    with _on_device(Q):
         if ranges is not None:
             assert ranges.col_lo.shape == (B, S_k) and ranges.col_hi.shape == (B, S_k) and ranges.row_lo.shape == (B, S_q)
         r = ranges
@@ -180,7 +203,7 @@ def flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_ca
         dq_acc = torch.empty((B, H, S_q, D), dtype=torch.float32, device=Q.device)
     assert dq_acc.dtype == torch.float32 and dq_acc.is_contiguous() and dq_acc.numel() == B * H * S_q * D
     st = _strides(Q, K, V, O, dO, dQ, dK, dV)
-    with torch.cuda.device(Q.device):
+    with _on_device(Q):
         rc = lib.fa_sm100_bwd_fused(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
                                     LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
                                     dq_acc.data_ptr(), B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
@@ -239,13 +262,16 @@ def flash_attention(Q, K, V, is_causal=False, *, sm_scale=None, ranges=None):
     return FlashAttentionFunction.apply(Q, K, V, is_causal, sm_scale, ranges)
 
 
-def flash_attention_varlen(q, k, v, cu_seqlens, is_causal=False, *, sm_scale=None):
+def flash_attention_varlen(q, k, v, cu_seqlens, is_causal=False, *, sm_scale=None, ranges=None):
     """Variable-length self-attention over PACKED sequences (the tutorial's own next step, Phase_6.md:160-174):
     q [total, H, D], k / v [total, Hk, D]; tokens cu_seqlens[s] .. cu_seqlens[s+1]-1 form sequence s.  Zero-copy: the packed
     buffers are addressed as one batch of length `total` through strided tensor maps, the block-diagonal mask is a Ranges
-    object and the kernels skip every tile that lies outside a sequence.  Returns O [total, H, D]."""
+    object and the kernels skip every tile that lies outside a sequence.  Returns O [total, H, D].
+    Building the Ranges from cu_seqlens costs a handful of tiny launches: pass ``ranges=Ranges.from_cu_seqlens(...)`` to reuse
+    one object across the layers of a model (cu_seqlens is then ignored)."""
     total = q.shape[0]
-    ranges = Ranges.from_cu_seqlens(cu_seqlens, total, device=q.device)
+    if ranges is None:
+        ranges = Ranges.from_cu_seqlens(cu_seqlens, total, device=q.device)
     O = flash_attention(q.transpose(0, 1)[None], k.transpose(0, 1)[None], v.transpose(0, 1)[None], is_causal,
                         sm_scale=sm_scale, ranges=ranges)
     return O[0].transpose(0, 1)
@@ -266,7 +292,7 @@ def flash_attention_delta(O, dO):
     lib = _cabi.load()
     B, H, S_q, D = O.shape
     delta = torch.empty((B, H, S_q), dtype=torch.float32, device=O.device)
-    with torch.cuda.device(O.device):
+    with _on_device(O):
         rc = lib.fa_sm100_delta(O.data_ptr(), dO.data_ptr(), delta.data_ptr(), B, H, S_q, D, _DT[O.dtype], _stream(O))
     _cabi.check("fa_sm100_delta", rc)
     return delta
@@ -281,7 +307,7 @@ def merge_partial_(O_acc, LSE_acc, O_part, LSE_part, q_off=0):
     assert O_acc.dtype == torch.float32 and LSE_acc.dtype == torch.float32 and LSE_part.dtype == torch.float32
     assert O_acc.is_contiguous() and O_part.is_contiguous() and LSE_acc.is_contiguous() and LSE_part.is_contiguous()
     assert O_acc.shape[:2] == O_part.shape[:2] and O_acc.shape[3] == D and LSE_acc.shape == O_acc.shape[:3]
-    with torch.cuda.device(O_part.device):
+    with _on_device(O_part):
         rc = lib.fa_sm100_merge(O_acc.data_ptr(), LSE_acc.data_ptr(), O_part.data_ptr(), LSE_part.data_ptr(),
                                 B, H, S_q, D, _DT[O_part.dtype], S_acc, int(q_off), _stream(O_part))
     _cabi.check("fa_sm100_merge", rc)
