@@ -21,6 +21,8 @@ SYMBOLS = {
     "fa_sm100_bwd_strided": (_i, [_vp] * 10 + [_i] * 8 + [_f, _vp, _vp, _i]),
     "fa_sm100_fwd_ranges": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "fa_sm100_bwd_ranges": (_i, [_vp] * 10 + [_i] * 8 + [_f, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "fa_sm100_fwd_opt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "fa_sm100_bwd_opt": (_i, [_vp] * 10 + [_i] * 8 + [_f, _vp, _vp, _vp, _i]),
     "fa_sm100_bwd_fused": (_i, [_vp] * 11 + [_i] * 8 + [_f, _vp, _vp, _i]),
     "fa_sm100_bwd_fused_workspace": (ctypes.c_size_t, [_i, _i, _i, _i]),
     "fa_sm100_bwd_parts": (_i, [_vp] * 10 + [_i] * 7 + [_f, _vp, _i]),
@@ -34,6 +36,12 @@ SYMBOLS = {
 }
 
 FA_DTYPE_FP16, FA_DTYPE_BF16 = 0, 1
+
+
+class Options(ctypes.Structure):
+    """struct fa_sm100_options (include/fa_sm100.h): range masks and dropout."""
+    _fields_ = [("row_lo", _vp), ("row_hi", _vp), ("col_lo", _vp), ("col_hi", _vp),
+                ("dropout_p", _f), ("dropout_seed", ctypes.c_ulonglong)]
 
 _lib = None
 

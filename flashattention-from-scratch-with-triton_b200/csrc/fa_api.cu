@@ -136,6 +136,18 @@ int heads_per_chunk(int n_heads, double bytes_per_head) {
 }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// dropout_p is quantised to 1/256 (one random byte per element): thresh = round(256 p), kept elements scale by 256 / (256 - thresh)
+int make_dropout(const fa_sm100_options* opt, DropoutParams* d) {
+    d->seed0 = d->seed1 = d->thresh = 0; d->scale = 1.f;
+    if (!opt || opt->dropout_p == 0.f) return 0;
+    if (!(opt->dropout_p > 0.f && opt->dropout_p < 1.f)) return fail(FA_ERR_SHAPE, "dropout_p %g not in [0, 1)", (double)opt->dropout_p);
+    unsigned int t = (unsigned int)lrintf(opt->dropout_p * 256.f);
+    if (t > 255u) t = 255u;
+    d->thresh = t; d->scale = 256.f / (256.f - (float)t);
+    d->seed0 = (uint32_t)(opt->dropout_seed & 0xffffffffull); d->seed1 = (uint32_t)(opt->dropout_seed >> 32);
+    return 0;
+}
+
 template <typename K> cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
@@ -154,7 +166,8 @@ int launch_fwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
 template <int D, bool kBf16>
 int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
                const FwdParams& p, int grid, cudaStream_t st) {
-    return p.row_lo ? launch_fwd_t<D, kBf16, true>(mq, mk, mv, mo, p, grid, st) : launch_fwd_t<D, kBf16, false>(mq, mk, mv, mo, p, grid, st);
+    return (p.row_lo || p.drop.thresh) ? launch_fwd_t<D, kBf16, true>(mq, mk, mv, mo, p, grid, st)
+                                       : launch_fwd_t<D, kBf16, false>(mq, mk, mv, mo, p, grid, st);
 }
 
 }  // namespace
@@ -194,6 +207,15 @@ int fa_sm100_fwd_strided(const void* q, const void* k, const void* v, void* o, f
 int fa_sm100_fwd_ranges(const void* q, const void* k, const void* v, void* o, float* lse,
                         int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                         const long long* strides, const int* row_lo, const int* row_hi, void* stream) {
+    fa_sm100_options opt = {row_lo, row_hi, nullptr, nullptr, 0.f, 0ull};
+    return fa_sm100_fwd_opt(q, k, v, o, lse, B, H, Hk, Sq, Sk, D, dtype, causal, sm_scale, strides, &opt, stream);
+}
+
+int fa_sm100_fwd_opt(const void* q, const void* k, const void* v, void* o, float* lse,
+                     int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                     const long long* strides, const fa_sm100_options* opt, void* stream) {
+    const int* row_lo = opt ? opt->row_lo : nullptr; const int* row_hi = opt ? opt->row_hi : nullptr;
+    DropoutParams drop; if (int rc = make_dropout(opt, &drop)) return rc;
     if (!q || !k || !v || !o || !lse) return fail(FA_ERR_NULL, "null tensor pointer");
     if ((row_lo == nullptr) != (row_hi == nullptr)) return fail(FA_ERR_NULL, "row_lo and row_hi must be given together");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
@@ -218,7 +240,7 @@ int fa_sm100_fwd_ranges(const void* q, const void* k, const void* v, void* o, fl
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse;
-    p.row_lo = row_lo; p.row_hi = row_hi;
+    p.row_lo = row_lo; p.row_hi = row_hi; p.drop = drop;
     p.sched = dev->sched_ring + (g_sched_next.fetch_add(1) % kSchedRing);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(p.sched, 0, sizeof(unsigned int), st);
@@ -279,6 +301,18 @@ int fa_sm100_bwd_ranges(const void* q, const void* k, const void* v, const void*
                         int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                         const long long* strides, const int* row_lo, const int* row_hi, const int* col_lo, const int* col_hi,
                         void* stream, int parts) {
+    fa_sm100_options opt = {row_lo, row_hi, col_lo, col_hi, 0.f, 0ull};
+    return fa_sm100_bwd_opt(q, k, v, o, dout, lse, dq, dk, dv, delta, B, H, Hk, Sq, Sk, D, dtype, causal, sm_scale, strides, &opt,
+                            stream, parts);
+}
+
+int fa_sm100_bwd_opt(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                     const float* lse, void* dq, void* dk, void* dv, float* delta,
+                     int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                     const long long* strides, const fa_sm100_options* opt, void* stream, int parts) {
+    const int* row_lo = opt ? opt->row_lo : nullptr; const int* row_hi = opt ? opt->row_hi : nullptr;
+    const int* col_lo = opt ? opt->col_lo : nullptr; const int* col_hi = opt ? opt->col_hi : nullptr;
+    DropoutParams drop; if (int rc = make_dropout(opt, &drop)) return rc;
     if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta) return fail(FA_ERR_NULL, "null tensor pointer");
     if (!row_lo != !row_hi || !row_lo != !col_lo || !row_lo != !col_hi)
         return fail(FA_ERR_NULL, "row_lo, row_hi, col_lo and col_hi must be given together");
@@ -316,7 +350,7 @@ int fa_sm100_bwd_ranges(const void* q, const void* k, const void* v, const void*
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;
-    p.row_lo = row_lo; p.row_hi = row_hi; p.col_lo = col_lo; p.col_hi = col_hi;
+    p.row_lo = row_lo; p.row_hi = row_hi; p.col_lo = col_lo; p.col_hi = col_hi; p.drop = drop;
     p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
     p.sms = dev->sms;
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
@@ -379,6 +413,7 @@ int fa_sm100_bwd_fused(const void* q, const void* k, const void* v, const void* 
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;
     p.row_lo = p.row_hi = p.col_lo = p.col_hi = nullptr;
+    p.drop.seed0 = p.drop.seed1 = p.drop.thresh = 0; p.drop.scale = 1.f;
     p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
     p.sms = dev->sms;
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);

@@ -43,6 +43,7 @@ struct BwdParams {
     // All four non-decreasing along the sequence; NULL = unrestricted.
     const int* row_lo; const int* row_hi;
     const int* col_lo; const int* col_hi;
+    DropoutParams drop;        // thresh = 0: no dropout (kDropout instantiations only)
 };
 
 // Turn-taking between the two math warpgroups around the exp loop (named barriers 3/4, as in the forward):
@@ -151,7 +152,9 @@ template <int D> struct DkvCfg {
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 32 + 1024;
 };
 
-template <int D, bool kBf16>
+// kDropout: instantiation that regenerates the forward's keep mask (fa_ptx.cuh): dV uses the dropped-out, rescaled P^T,
+// dP is masked and rescaled before dS = P o (dP - delta).  The plain instantiation is untouched.
+template <int D, bool kBf16, bool kDropout = false>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                   const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
@@ -421,12 +424,14 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 q_lo = max(q_lo, __ldg(p.col_lo + ci)); q_hi = min(q_hi, __ldg(p.col_hi + ci));
             }
             int qtile = i_start;                          // q tile of the current iteration (wraps per query head of the group)
+            uint32_t bhq = (uint32_t)((bh / p.Hk) * p.H + (bh % p.Hk) * p.G);   // batch*H + query head of the current iteration
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it;
                 const uint32_t ss = g % C::kStatStages;
                 const uint32_t stat = smem_u32(sStat) + ss * 1024 + h * 256;
                 const int q0 = qtile * 128 + h * 64;                 // global query index of my column 0
-                if (++qtile == i_end) qtile = i_start;
+                const uint32_t bhq_it = bhq;
+                if (++qtile == i_end) { qtile = i_start; ++bhq; }
                 mbar_wait(&stat_full[ss], (g / C::kStatStages) & 1, 430);
                 const uint32_t tSTi = tST + (kDoubleS ? (g & 1) * 128 : 0);
                 if (kDoubleS) mbar_wait((g & 1) ? s_full1 : s_full, (g >> 1) & 1, 431);
@@ -459,11 +464,26 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     #pragma unroll
                     for (int c = 0; c < 64; ++c) if (c < cmin || c > cmax) pv[c] = 0.f;
                 }
+                uint64_t keep = ~0ull;                       // keep bit per column (query) of my kv row
+                if constexpr (kDropout) {
+                    keep = 0ull;
+                    #pragma unroll
+                    for (int c = 0; c < 64; ++c) {
+                        const uint32_t w = dropout_word(dropout_row_key(p.drop.seed0, bhq_it, (uint32_t)(q0 + c)), p.drop.seed1, (uint32_t)kv_g >> 2);
+                        keep |= (uint64_t)dropout_keep(w, (uint32_t)kv_g, p.drop.thresh) << c;
+                    }
+                }
                 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     uint32_t pk[16];
                     #pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = pack2<kBf16>(pv[q * 32 + 2 * i], pv[q * 32 + 2 * i + 1]);
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = q * 32 + 2 * i;
+                        if constexpr (kDropout)                  // dV sees the dropped-out, rescaled P^T; pv keeps P for dS
+                            pk[i] = pack2<kBf16>(((keep >> c) & 1) ? pv[c] * p.drop.scale : 0.f, ((keep >> (c + 1)) & 1) ? pv[c + 1] * p.drop.scale : 0.f);
+                        else
+                            pk[i] = pack2<kBf16>(pv[c], pv[c + 1]);
+                    }
                     tmem_st16(tSTi + q * 16, pk);
                 }
                 tc_wait_st(); tc_fence_before();
@@ -482,10 +502,14 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                             const int c = q * 32 + 2 * i;
                             const float4 dl = lds128(stat + 512 + c * 4);
                             float d0, d1, d2, d3;        // dS = P o (dP - delta), packed: FADD2 + FMUL2
-                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]),
-                                            fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), pack_f2(dl.x, dl.y))), d0, d1);
-                            unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]),
-                                            fadd2(pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]), pack_f2(dl.z, dl.w))), d2, d3);
+                            uint64_t dpa = pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), dpb = pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]);
+                            if constexpr (kDropout) {
+                                float e0, e1, e2, e3; unpack_f2(dpa, e0, e1); unpack_f2(dpb, e2, e3);
+                                dpa = pack_f2(((keep >> c) & 1) ? e0 * p.drop.scale : 0.f, ((keep >> (c + 1)) & 1) ? e1 * p.drop.scale : 0.f);
+                                dpb = pack_f2(((keep >> (c + 2)) & 1) ? e2 * p.drop.scale : 0.f, ((keep >> (c + 3)) & 1) ? e3 * p.drop.scale : 0.f);
+                            }
+                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), fadd2(dpa, pack_f2(dl.x, dl.y))), d0, d1);
+                            unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]), fadd2(dpb, pack_f2(dl.z, dl.w))), d2, d3);
                             pk[i] = pack2<kBf16>(d0, d1); pk[i + 1] = pack2<kBf16>(d2, d3);
                         }
                         tmem_st16(tDPT + q * 16, pk);
@@ -547,7 +571,7 @@ template <int D> struct DqCfg {
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 32 + 1024;
 };
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, bool kDropout = false>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
@@ -716,6 +740,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 const size_t ri = (size_t)(bh / p.H) * p.Sq + min(row_g, p.Sq - 1);
                 k_lo = __ldg(p.row_lo + ri); k_hi = min(__ldg(p.row_hi + ri), p.Sk);
             }
+            const uint32_t drop_key = kDropout ? dropout_row_key(p.drop.seed0, (uint32_t)bh, (uint32_t)row_g) : 0u;
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it;
                 mbar_wait(s_full, g & 1, 530);
@@ -767,7 +792,16 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         for (int i = 0; i < 16; ++i) {
                             const int c = q * 32 + 2 * i;
                             float d0, d1;
-                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), ndl)), d0, d1);
+                            uint64_t dpv = pack_u2(dp[q][2 * i], dp[q][2 * i + 1]);
+                            if constexpr (kDropout) {               // dP reaches P only through the kept, rescaled elements
+                                const uint32_t kcol = (uint32_t)(k0 + c);
+                                const uint32_t w = dropout_word(drop_key, p.drop.seed1, kcol >> 2);
+                                float e0, e1; unpack_f2(dpv, e0, e1);
+                                e0 = dropout_keep(w, kcol, p.drop.thresh) ? e0 * p.drop.scale : 0.f;
+                                e1 = dropout_keep(w, kcol + 1, p.drop.thresh) ? e1 * p.drop.scale : 0.f;
+                                dpv = pack_f2(e0, e1);
+                            }
+                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), fadd2(dpv, ndl)), d0, d1);
                             pk[i] = pack2<kBf16>(d0, d1);
                         }
                         tmem_st16(tDS + (g & 1) * 64 + q * 16, pk);
@@ -803,15 +837,15 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
-template <int D, bool kBf16>
-int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
-                 const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
-                 int parts, cudaStream_t st) {
+template <int D, bool kBf16, bool kDropout>
+int launch_bwd_td(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
+                  const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
+                  int parts, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(fa_bwd_dkv_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg<D>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(fa_bwd_dkv_kernel<D, kBf16, kDropout>, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(fa_bwd_dq_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D>::kSmemBytes);
+        e = cudaFuncSetAttribute(fa_bwd_dq_kernel<D, kBf16, kDropout>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
@@ -819,16 +853,23 @@ int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
     if (parts & 2) {
         const int items = p.BH * p.n_qtiles;
         const int grid = FA_BWD_PERSISTENT ? (items < p.sms ? items : p.sms) : items;
-        fa_bwd_dq_kernel<D, kBf16><<<grid, kBwdThreads, DqCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
+        fa_bwd_dq_kernel<D, kBf16, kDropout><<<grid, kBwdThreads, DqCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
     if (parts & 4) {
         const int items = (p.BH / p.G) * p.n_ktiles;
         const int grid = FA_BWD_PERSISTENT ? (items < p.sms ? items : p.sms) : items;
-        fa_bwd_dkv_kernel<D, kBf16><<<grid, kBwdThreads, DkvCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
+        fa_bwd_dkv_kernel<D, kBf16, kDropout><<<grid, kBwdThreads, DkvCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
     }
     return (int)cudaGetLastError();
+}
+template <int D, bool kBf16>
+int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
+                 const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
+                 int parts, cudaStream_t st) {
+    return p.drop.thresh ? launch_bwd_td<D, kBf16, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, parts, st)
+                         : launch_bwd_td<D, kBf16, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, parts, st);
 }
 
 inline int launch_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,

@@ -394,6 +394,29 @@ __device__ __forceinline__ void tma_load_4d_e(void* dst, const CUtensorMap* m, u
                  :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// ----------------------------------------------------------------------------------------------
+// Dropout (the tutorial's own next step, Phase_6.md:54-114): a counter-based generator keyed by (seed, batch*head, query row,
+// key column), so the forward and both backward kernels regenerate the same keep mask in whatever orientation they hold the
+// score tile.  One 32-bit word covers the 4 key columns k & ~3 .. (k | 3) of one query row, one byte per element;
+// keep <=> byte >= thresh, i.e. p_drop = thresh / 256 exactly and kept elements are scaled by 256 / (256 - thresh).
+// mix32 is the "lowbias32" integer finaliser.  The test suite pins this definition with a numpy restatement (dropout_keep_mask).
+// ----------------------------------------------------------------------------------------------
+struct DropoutParams { uint32_t seed0, seed1, thresh; float scale; };
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_row_key(uint32_t seed0, uint32_t bh, uint32_t q) {
+    return mix32((bh * 0x9E3779B1u + q) ^ seed0);
+}
+// the 4 random bytes of key columns 4*k4 .. 4*k4+3 of the row with key `row_key`
+__host__ __device__ __forceinline__ uint32_t dropout_word(uint32_t row_key, uint32_t seed1, uint32_t k4) {
+    return mix32(row_key ^ (k4 * 0x85EBCA6Bu + seed1));
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t word, uint32_t k, uint32_t thresh) {
+    return ((word >> ((k & 3u) * 8u)) & 0xffu) >= thresh;
+}
+
 // Work order of the persistent kernels.  Heads are cut into chunks of `hc` heads whose tensors fit L2 together; inside a
 // chunk items go tile-major (t = 0 is the heaviest tile under causal), so the dynamic scheduler hands out heavy items first
 // and the last items of a launch are the lightest.  (A plain head-major order leaves one of the heaviest items of the last

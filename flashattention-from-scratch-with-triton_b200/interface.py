@@ -118,11 +118,21 @@ class Ranges:
         return self.row_lo, self.row_hi
 
 
-def _rp(t):
-    return t.data_ptr() if t is not None else None
+def _options(ranges, dropout_p, dropout_seed, backward=False):
+    """ctypes fa_sm100_options (or None for the plain operator)."""
+    if ranges is None and not dropout_p:
+        return None
+    o = _cabi.Options()
+    if ranges is not None:
+        o.row_lo, o.row_hi = ranges.row_lo.data_ptr(), ranges.row_hi.data_ptr()
+        if backward:
+            o.col_lo, o.col_hi = ranges.col_lo.data_ptr(), ranges.col_hi.data_ptr()
+    o.dropout_p = float(dropout_p or 0.0)
+    o.dropout_seed = int(dropout_seed or 0) & 0xFFFFFFFFFFFFFFFF
+    return ctypes.byref(o)
 
 
-def flash_attention_forward(Q, K, V, is_causal, sm_scale=None, ranges=None):
+def flash_attention_forward(Q, K, V, is_causal, sm_scale=None, ranges=None, dropout_p=0.0, dropout_seed=0):
     """Allocate O / LSE and launch the forward kernel (reference :14-60).
 
     Q: [B,H,S_q,D], K,V: [B,H,S_k,D] CUDA fp16/bf16, contiguous or TMA-compatible strided views.  Returns
@@ -139,18 +149,19 @@ def flash_attention_forward(Q, K, V, is_causal, sm_scale=None, ranges=None):
     with _on_device(Q):
         if ranges is not None:
             assert ranges.row_lo.shape == (B, S_q) and ranges.row_hi.shape == (B, S_q) and ranges.row_lo.device == Q.device
-        rc = lib.fa_sm100_fwd_ranges(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), LSE.data_ptr(),
-                                     B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
-                                     float(sm_scale) if sm_scale is not None else 0.0, st,
-                                     _rp(ranges.row_lo if ranges else None), _rp(ranges.row_hi if ranges else None), _stream(Q))
-    _cabi.check("fa_sm100_fwd_ranges", rc)
+        rc = lib.fa_sm100_fwd_opt(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), LSE.data_ptr(),
+                                  B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                  float(sm_scale) if sm_scale is not None else 0.0, st,
+                                  _options(ranges, dropout_p, dropout_seed), _stream(Q))
+    _cabi.check("fa_sm100_fwd_opt", rc)
     return O, LSE
 
 
 BWD_DELTA, BWD_DQ, BWD_DKV = 1, 2, 4
 
 
-def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, parts, sm_scale=None, ranges=None):
+def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, parts, sm_scale=None, ranges=None,
+                                   dropout_p=0.0, dropout_seed=0):
     """Launch a subset of the backward kernels into caller-provided outputs (per-kernel timing, ring hops)."""
     lib = _cabi.load()
     B, H, S_q, D = Q.shape
@@ -159,14 +170,12 @@ def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_ca
     with _on_device(Q):
         if ranges is not None:
             assert ranges.col_lo.shape == (B, S_k) and ranges.col_hi.shape == (B, S_k) and ranges.row_lo.shape == (B, S_q)
-        r = ranges
-        rc = lib.fa_sm100_bwd_ranges(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
-                                     LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
-                                     B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
-                                     float(sm_scale) if sm_scale is not None else 0.0, st,
-                                     _rp(r.row_lo if r else None), _rp(r.row_hi if r else None), _rp(r.col_lo if r else None),
-                                     _rp(r.col_hi if r else None), _stream(Q), int(parts))
-    _cabi.check("fa_sm100_bwd_ranges", rc)
+        rc = lib.fa_sm100_bwd_opt(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
+                                  LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
+                                  B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                  float(sm_scale) if sm_scale is not None else 0.0, st,
+                                  _options(ranges, dropout_p, dropout_seed, backward=True), _stream(Q), int(parts))
+    _cabi.check("fa_sm100_bwd_opt", rc)
 
 
 # Backward algorithm.  Head dim 64 defaults to the fused single-pass kernel (5 GEMMs and one exponential per score
@@ -216,16 +225,16 @@ def _empty_like_kernel(t):
     return e if tma_compatible(e) else torch.empty(t.shape, dtype=t.dtype, device=t.device)
 
 
-def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None, ranges=None):
+def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None, ranges=None, dropout_p=0.0, dropout_seed=0):
     """Allocate dQ / dK / dV (+ fp32 delta) and launch the backward kernels (reference :62-128)."""
     B, H, S_q, D = Q.shape
     dQ, dK, dV = _empty_like_kernel(Q), _empty_like_kernel(K), _empty_like_kernel(V)      # reference :71-73
     delta = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
-    if fused_backward_supported(Q) and not _deterministic and ranges is None:
+    if fused_backward_supported(Q) and not _deterministic and ranges is None and not dropout_p:
         flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale)
-    else:                                                  # range masks run on the two-kernel path
+    else:                                                  # range masks and dropout run on the two-kernel path
         flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, BWD_DELTA | BWD_DQ | BWD_DKV, sm_scale,
-                                       ranges)
+                                       ranges, dropout_p, dropout_seed)
     return dQ, dK, dV
 
 
@@ -233,7 +242,7 @@ class FlashAttentionFunction(torch.autograd.Function):
     """Same contract as the reference class (reference :130-166)."""
 
     @staticmethod
-    def forward(ctx, Q, K, V, is_causal: bool, sm_scale=None, ranges=None):
+    def forward(ctx, Q, K, V, is_causal: bool, sm_scale=None, ranges=None, dropout_p=0.0, dropout_seed=0):
         assert Q.is_cuda and K.is_cuda and V.is_cuda                       # :133
         assert Q.dtype in (torch.float16, torch.bfloat16)                  # :134
         assert Q.shape[-1] == K.shape[-1] == V.shape[-1]                   # :135
@@ -241,25 +250,30 @@ class FlashAttentionFunction(torch.autograd.Function):
         assert K.dtype == Q.dtype and V.dtype == Q.dtype
         assert K.shape[:3] == V.shape[:3] and K.shape[0] == Q.shape[0] and Q.shape[1] % K.shape[1] == 0   # GQA/MQA: Hk | H
         Q_ = as_kernel_layout(Q); K_ = as_kernel_layout(K); V_ = as_kernel_layout(V)   # :138-140, without needless copies
-        O, LSE = flash_attention_forward(Q_, K_, V_, is_causal, sm_scale, ranges)
+        O, LSE = flash_attention_forward(Q_, K_, V_, is_causal, sm_scale, ranges, dropout_p, dropout_seed)
         ctx.save_for_backward(Q_, K_, V_, O, LSE)                          # :145 (same set, same order)
         ctx.is_causal = is_causal                                          # :147
         ctx.sm_scale = sm_scale
         ctx.ranges = ranges
+        ctx.dropout = (dropout_p, dropout_seed)           # the backward regenerates the keep mask from the same seed
         return O
 
     @staticmethod
     def backward(ctx, dO):
         Q, K, V, O, LSE = ctx.saved_tensors                                # :154
         dO_ = as_kernel_layout(dO)                                         # :156
-        dQ, dK, dV = flash_attention_backward(Q, K, V, O, dO_, LSE, ctx.is_causal, ctx.sm_scale, ctx.ranges)
-        return dQ, dK, dV, None, None, None                                # :166 (+None for sm_scale, ranges)
+        dQ, dK, dV = flash_attention_backward(Q, K, V, O, dO_, LSE, ctx.is_causal, ctx.sm_scale, ctx.ranges, *ctx.dropout)
+        return dQ, dK, dV, None, None, None, None, None                    # :166 (+None for every added argument)
 
 
-def flash_attention(Q, K, V, is_causal=False, *, sm_scale=None, ranges=None):
+def flash_attention(Q, K, V, is_causal=False, *, sm_scale=None, ranges=None, dropout_p=0.0, dropout_seed=None):
     """O = softmax(Q K^T * scale [+ causal mask]) V, differentiable w.r.t. Q, K, V (reference :169-170).
-    ``ranges`` (a Ranges object) adds a per-row key-range mask: packed sequences, key padding, sliding windows."""
-    return FlashAttentionFunction.apply(Q, K, V, is_causal, sm_scale, ranges)
+    ``ranges`` (a Ranges object) adds a per-row key-range mask: packed sequences, key padding, sliding windows.
+    ``dropout_p`` > 0 drops attention probabilities (quantised to 1/256, kept ones scaled by 1/(1-p)); the mask is a pure
+    function of ``dropout_seed`` (drawn from torch's CPU generator when None) and the element's coordinates."""
+    if dropout_p and dropout_seed is None:
+        dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return FlashAttentionFunction.apply(Q, K, V, is_causal, sm_scale, ranges, float(dropout_p or 0.0), dropout_seed or 0)
 
 
 def flash_attention_varlen(q, k, v, cu_seqlens, is_causal=False, *, sm_scale=None, ranges=None):

@@ -100,6 +100,25 @@ int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* 
                        int B, int H, int Sq, int Sk, int D, int dtype, int causal,
                        float sm_scale, void* stream, int parts);
 
+/* Everything optional in one struct (NULL = the plain operator): the range masks above and dropout — the tutorial's other
+ * "next step" (Phase_6.md:54-114).  Each attention probability is kept with probability 1 - p and scaled by 1 / (1 - p); p is
+ * quantised to thresh / 256 (one random byte per element).  The keep mask is a pure function of (dropout_seed, batch * H + head,
+ * query row, key column) — mix32 / dropout_word in csrc/fa_ptx.cuh; the tests pin it with a numpy restatement — so the backward
+ * regenerates it from the same seed; LSE is that of the undropped softmax.  The backward with dropout is the two-kernel path. */
+typedef struct fa_sm100_options {
+    const int* row_lo; const int* row_hi;       /* [B,Sq] or NULL */
+    const int* col_lo; const int* col_hi;       /* [B,Sk] or NULL (backward only) */
+    float dropout_p;                            /* 0 = off; must be < 1 */
+    unsigned long long dropout_seed;
+} fa_sm100_options;
+int fa_sm100_fwd_opt(const void* q, const void* k, const void* v, void* o, float* lse,
+                     int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                     const long long* strides, const fa_sm100_options* opt, void* stream);
+int fa_sm100_bwd_opt(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                     const float* lse, void* dq, void* dk, void* dv, float* delta,
+                     int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                     const long long* strides, const fa_sm100_options* opt, void* stream, int parts);
+
 /* Fused single-pass backward, head dim 64 only: one kernel computes dK, dV and dQ with 5 GEMMs per
  * (kv tile, q tile) pair and one exponential per score element, instead of the dQ + dK/dV kernel pair above
  * (reference launcher code/My_FlashAttention_optimized.py:111-126: 7 GEMMs, two exponentials).  dQ partials are summed over kv

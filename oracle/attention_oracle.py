@@ -158,8 +158,31 @@ def backward_blocked(Q, K, V, O, dO, LSE, is_causal, BLOCK_M=64, BLOCK_N=64, sm_
     return dQ, dK, dV, delta
 
 
+def dropout_keep_mask(seed: int, B: int, H: int, S_q: int, S_k: int, dropout_p: float):
+    """The keep mask and scale of the CUDA kernels' dropout (csrc/fa_ptx.cuh: mix32 / dropout_row_key / dropout_word /
+    dropout_keep), restated with numpy uint32 arithmetic.  Returns (keep bool [B,H,S_q,S_k], scale)."""
+    import numpy as np
+    thresh = min(int(round(dropout_p * 256.0)), 255)
+    M = np.uint32
+
+    def mix32(x):
+        x = x ^ (x >> M(16)); x = x * M(0x7FEB352D); x = x ^ (x >> M(15)); x = x * M(0x846CA68B); x = x ^ (x >> M(16))
+        return x
+    seed0, seed1 = M(seed & 0xFFFFFFFF), M((seed >> 32) & 0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        bh = np.arange(B * H, dtype=np.uint32)[:, None]
+        q = np.arange(S_q, dtype=np.uint32)[None, :]
+        row_key = mix32((bh * M(0x9E3779B1) + q) ^ seed0)                               # [BH, S_q]
+        k = np.arange(S_k, dtype=np.uint32)
+        word = mix32(row_key[:, :, None] ^ ((k >> M(2)) * M(0x85EBCA6B) + seed1)[None, None, :])   # [BH, S_q, S_k]
+        byte = (word >> ((k & M(3)) * M(8))[None, None, :]) & M(0xFF)
+    keep = torch.from_numpy((byte >= thresh).reshape(B, H, S_q, S_k))
+    return keep, 256.0 / (256.0 - thresh)
+
+
 def closed_form(Q, K, V, dO=None, is_causal: bool = False, sm_scale: Optional[float] = None,
-                dtype: torch.dtype = torch.float64, q_offset: int = 0, k_offset: int = 0, row_ranges=None):
+                dtype: torch.dtype = torch.float64, q_offset: int = 0, k_offset: int = 0, row_ranges=None,
+                keep_mask=None, keep_scale: float = 1.0):
     """Exact (materialised-scores) attention in ``dtype`` — no tiling, no 16-bit rounding.
 
     Forward: Phase_3.md:699-708 (LSE = logsumexp of masked, scaled scores).
@@ -169,6 +192,8 @@ def closed_form(Q, K, V, dO=None, is_causal: bool = False, sm_scale: Optional[fl
     (ring hops).  Fully-masked rows give O = 0, LSE = −inf.
     ``row_ranges`` = (lo, hi), int tensors [B, S_q]: query row i additionally sees only keys lo[b,i] <= j < hi[b,i]
     (packed variable-length sequences as in Phase_6.md:160-174, key padding, sliding windows).
+    ``keep_mask`` [B,H,S_q,S_k] / ``keep_scale``: dropout on the attention probabilities (Phase_6.md:54-114):
+    O = (P o keep * scale) V; the same mask scales dP in the backward; LSE and delta are unaffected.
     """
     D = Q.shape[-1]
     scale = 1.0 / math.sqrt(D) if sm_scale is None else sm_scale
@@ -186,12 +211,15 @@ def closed_form(Q, K, V, dO=None, is_causal: bool = False, sm_scale: Optional[fl
     LSE = torch.logsumexp(S, dim=-1)
     P = torch.exp(S - LSE[..., None])
     P = torch.nan_to_num(P, nan=0.0)           # fully masked rows: exp(-inf - -inf)
-    O = torch.matmul(P, v)
+    Pd = P if keep_mask is None else P * keep_mask.to(dtype) * keep_scale
+    O = torch.matmul(Pd, v)
     if dO is None:
         return O, LSE
     do = dO.to(dtype)
-    dV = torch.matmul(P.transpose(-1, -2), do)
+    dV = torch.matmul(Pd.transpose(-1, -2), do)
     dP = torch.matmul(do, v.transpose(-1, -2))
+    if keep_mask is not None:
+        dP = dP * keep_mask.to(dtype) * keep_scale
     delta = (do * O).sum(dim=-1)
     dS = P * (dP - delta[..., None])
     dQ = torch.matmul(dS, k) * scale

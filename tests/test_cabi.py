@@ -65,6 +65,11 @@ def test_argument_validation_without_gpu(lib):
     # range masks: lo / hi arrays come in pairs (quadruples for the backward)
     assert lib.fa_sm100_fwd_ranges(p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, None, p, None, None) == -1
     assert lib.fa_sm100_bwd_ranges(p, p, p, p, p, p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, None, p, p, p, None, None, 7) == -1
+    # options struct: dropout_p must be in [0, 1)
+    import flashattn_b200._cabi as cabi
+    opt = cabi.Options(); opt.dropout_p = 1.0
+    assert lib.fa_sm100_fwd_opt(p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, None, ctypes.byref(opt), None) == -4
+    assert b"dropout" in lib.fa_last_error()
     assert lib.fa_sm100_delta(p, None, p, 1, 1, 128, 64, 1, None) == -1
     assert lib.fa_sm100_merge(p, p, p, None, 1, 1, 128, 64, 1, 128, 0, None) == -1
     assert lib.fa_sm100_merge(p, p, p, p, 1, 1, 128, 64, 1, 128, 64, None) == -4

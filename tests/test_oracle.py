@@ -114,3 +114,24 @@ def test_range_mask_oracle_and_helpers():
         assert torch.equal(from_rows, from_cols)
         for t in (rr.row_lo, rr.row_hi, rr.col_lo, rr.col_hi):
             assert (t[:, 1:] >= t[:, :-1]).all()         # monotone: the kernels take tile ranges from first / last rows
+
+
+def test_dropout_mask_restatement():
+    """dropout_keep_mask: keep rate = 1 - thresh/256, deterministic in the seed, and dropout in the closed form keeps the
+    expectation (E[O_drop] = O) — the property the 1/(1-p) rescale exists for."""
+    k1, s1 = orc.dropout_keep_mask(7, 2, 3, 96, 160, 0.25)
+    k2, _ = orc.dropout_keep_mask(7, 2, 3, 96, 160, 0.25)
+    k3, _ = orc.dropout_keep_mask(8, 2, 3, 96, 160, 0.25)
+    assert torch.equal(k1, k2) and not torch.equal(k1, k3) and abs(s1 - 4 / 3) < 1e-12
+    assert abs(k1.float().mean().item() - 0.75) < 5e-3
+    assert (k1.float().mean(dim=(0, 1, 2)) - 0.75).abs().max() < 0.08          # no dead key columns
+    assert orc.dropout_keep_mask(7, 1, 1, 8, 8, 0.0)[0].all()
+    g = torch.Generator().manual_seed(5)
+    Q, K, V = (torch.randn(1, 1, 32, 16, generator=g) for _ in range(3))
+    O = orc.closed_form(Q, K, V)[0]
+    acc = torch.zeros_like(O)
+    n = 400
+    for seed in range(n):
+        keep, sc = orc.dropout_keep_mask(seed, 1, 1, 32, 32, 0.5)
+        acc += orc.closed_form(Q, K, V, keep_mask=keep, keep_scale=sc)[0]
+    assert (acc / n - O).abs().max() < 0.12
