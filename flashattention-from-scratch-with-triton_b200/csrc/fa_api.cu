@@ -94,6 +94,10 @@ __device__ unsigned int g_sched_ring[kSchedRing];
 DeviceInfo g_dev[kMaxDevices];
 std::mutex g_dev_mu;
 std::atomic<unsigned int> g_sched_next{0};
+// `pairs` consecutive {work counter, retired-CTA counter} pairs from the ring (zero at load time, self-resetting afterwards)
+unsigned int sched_slot(unsigned int pairs) {
+    return (g_sched_next.fetch_add(pairs) % (kSchedRing / 2 - pairs)) * 2;
+}
 
 int device_info(DeviceInfo** out) {
     int dev = 0;
@@ -241,10 +245,8 @@ int fa_sm100_fwd_opt(const void* q, const void* k, const void* v, void* o, float
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse;
     p.row_lo = row_lo; p.row_hi = row_hi; p.drop = drop;
-    p.sched = dev->sched_ring + (g_sched_next.fetch_add(1) % kSchedRing);
+    p.sched = dev->sched_ring + sched_slot(1);          // self-resetting counter pair (sched_retire): no memset on the stream
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(p.sched, 0, sizeof(unsigned int), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(sched)");
     const int grid = p.n_items < dev->sms ? p.n_items : dev->sms;
     if (D == 64) return dtype ? launch_fwd<64, true>(mq, mk, mv, mo, p, grid, st) : launch_fwd<64, false>(mq, mk, mv, mo, p, grid, st);
     return dtype ? launch_fwd<128, true>(mq, mk, mv, mo, p, grid, st) : launch_fwd<128, false>(mq, mk, mv, mo, p, grid, st);
@@ -355,11 +357,9 @@ int fa_sm100_bwd_opt(const void* q, const void* k, const void* v, const void* o,
     p.sms = dev->sms;
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
     p.hc_dkv = heads_per_chunk(BH / p.G, 4.0 * ((double)p.G * Sq + Sk) * D);
-    {   // two scheduler counters from the ring, zeroed on the stream ahead of the kernels
-        const unsigned int slot = g_sched_next.fetch_add(2) % (kSchedRing - 1);
-        p.sched_dkv = dev->sched_ring + slot; p.sched_dq = dev->sched_ring + slot + 1;
-        cudaError_t e = cudaMemsetAsync(p.sched_dkv, 0, 2 * sizeof(unsigned int), st);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(sched)");
+    {   // two self-resetting counter pairs from the ring
+        const unsigned int slot = sched_slot(2);
+        p.sched_dkv = dev->sched_ring + slot; p.sched_dq = dev->sched_ring + slot + 2;
     }
     rc = launch_bwd(mq, mk, mv, mdo, mdq, mdk, mdv, p, D, dtype, parts, st);
     g_launches += ((parts & FA_BWD_DQ) ? 1 : 0) + ((parts & FA_BWD_DKV) ? 1 : 0);
@@ -418,9 +418,7 @@ int fa_sm100_bwd_fused(const void* q, const void* k, const void* v, const void* 
     p.sms = dev->sms;
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
     p.hc_dkv = heads_per_chunk(BH / p.G, 4.0 * ((double)p.G * Sq + Sk) * D);
-    p.sched_dkv = dev->sched_ring + (g_sched_next.fetch_add(1) % kSchedRing); p.sched_dq = nullptr;
-    cudaError_t e = cudaMemsetAsync(p.sched_dkv, 0, sizeof(unsigned int), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(sched)");
+    p.sched_dkv = dev->sched_ring + sched_slot(1); p.sched_dq = nullptr;
     rc = dtype ? launch_bwd_fused_t<true>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts)
                : launch_bwd_fused_t<false>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts);
     g_launches += ((parts & FA_BWD_FUSED) ? 1 : 0) + ((parts & FA_BWD_CONVERT) ? 1 : 0);

@@ -342,6 +342,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dkv, 1u) + (int)gridDim.x : n_items;
                 item = __shfl_sync(0xffffffffu, item, 0);
             }
+            if (lane_id() == 0) sched_retire(p.sched_dkv);
         }
     } else if (warp == 8) {
         // ---------------------------------- MMA issuer ----------------------------------
@@ -673,6 +674,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dq, 1u) + (int)gridDim.x : n_items;
             item = __shfl_sync(0xffffffffu, item, 0);
         }
+        if (lane_id() == 0) sched_retire(p.sched_dq);
     } else if (warp == 8) {
         // ---------------------------------- MMA issuer (whole warp, converged) ----------------------------------
         reg_dealloc<BwdRegs<D>::kOther>();

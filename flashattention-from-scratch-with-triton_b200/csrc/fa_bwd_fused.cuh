@@ -293,6 +293,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             if (lane_id() == 0) item = (int)atomicAdd(p.sched_dkv, 1u) + (int)gridDim.x;
             item = __shfl_sync(0xffffffffu, item, 0);
         }
+        if (lane_id() == 0) sched_retire(p.sched_dkv);
     } else if (warp == 8) {
         // ---------------------------------- MMA issuer (whole warp, converged) ----------------------------------
         reg_dealloc<BwdRegs<D>::kOther>();

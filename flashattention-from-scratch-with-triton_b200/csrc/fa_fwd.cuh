@@ -205,6 +205,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 if (lane_id() == 0) item = (int)atomicAdd(p.sched, 1u) + (int)gridDim.x;
                 item = __shfl_sync(0xffffffffu, item, 0);
             }
+            if (lane_id() == 0) sched_retire(p.sched);
         }
     } else if (warp == 8 || warp == 10) {
         // ===================================== MMA issuers =====================================

@@ -429,6 +429,13 @@ __device__ __forceinline__ void item_to_head_tile(int item, int n_heads, int n_t
     t = rem / nh; head = h0 + rem - t * nh;
 }
 
+// The work counters of the persistent kernels reset themselves, so no memset has to precede a launch: word 0 hands out items,
+// word 1 counts the CTAs whose scheduler warp has drawn its last item (>= n_items); the last of them zeroes both.  Every fetch on
+// word 0 has returned by then, and the next user of the slot is a later launch.
+__device__ __forceinline__ void sched_retire(unsigned int* sched) {
+    if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
+}
+
 // register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it)
 template <int N> __device__ __forceinline__ void reg_alloc()   { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
