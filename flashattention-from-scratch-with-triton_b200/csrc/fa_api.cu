@@ -162,9 +162,9 @@ int launch_fwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
     static std::once_flag once; static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] { attr_err = set_smem(fa_fwd_kernel<D, kBf16, kRanges>, FwdCfg<D>::kSmemBytes); });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(fwd smem)");
-    fa_fwd_kernel<D, kBf16, kRanges><<<grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mo, p);
+    cudaError_t e = launch_pdl(fa_fwd_kernel<D, kBf16, kRanges>, grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st, mq, mk, mv, mo, p);
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd_kernel launch");
 }
 template <int D, bool kBf16>

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) fa_delta_kernel(const uint4* __restrict__
     constexpr int U = 4;                             // rows per thread per iteration
     const int sub = threadIdx.x % TPR;
     const long long stride = (long long)gridDim.x * RPB;
+    pdl_wait();
     for (long long row0 = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row0 < rows; row0 += stride * U) {
         uint4 a[U], b[U];
         #pragma unroll
@@ -81,10 +82,10 @@ inline int launch_delta(const void* o, const void* dout, float* delta, long long
     const long long cap = (long long)sms * 8;
     if (blocks > cap) blocks = cap;
     const uint4* o4 = (const uint4*)o; const uint4* d4 = (const uint4*)dout;
-    if (D == 64) { if (dtype) fa_delta_kernel<64, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc);
-                   else fa_delta_kernel<64, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc); }
-    else         { if (dtype) fa_delta_kernel<128, true><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc);
-                   else fa_delta_kernel<128, false><<<(int)blocks, 256, 0, st>>>(o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc); }
+    if (D == 64) { if (dtype) launch_pdl(fa_delta_kernel<64, true>, (int)blocks, 256, 0, st, o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc);
+                   else launch_pdl(fa_delta_kernel<64, false>, (int)blocks, 256, 0, st, o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc); }
+    else         { if (dtype) launch_pdl(fa_delta_kernel<128, true>, (int)blocks, 256, 0, st, o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc);
+                   else launch_pdl(fa_delta_kernel<128, false>, (int)blocks, 256, 0, st, o4, d4, delta, rows, H, Sq, so, sd, (float4*)zero_acc); }
     return (int)cudaGetLastError();
 }
 
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) fa_merge_kernel(float4* __restrict__ o_ac
     constexpr int TPR = D / 8;
     constexpr int RPB = 256 / TPR;
     const int sub = threadIdx.x % TPR;
+    pdl_wait();
     for (long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row < rows; row += (long long)gridDim.x * RPB) {
         const long long arow = (row / Sq) * Sq_acc + q_off + (row % Sq);     // row inside the accumulator
         const float la = lse_acc[arow], lb = lse_part[row];
@@ -127,10 +129,10 @@ inline int launch_merge(float* o_acc, float* lse_acc, const void* o_part, const 
     const long long cap = (long long)sms * 16;
     if (blocks > cap) blocks = cap;
     float4* oa = (float4*)o_acc; const uint4* op = (const uint4*)o_part;
-    if (D == 64) { if (dtype) fa_merge_kernel<64, true><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off);
-                   else fa_merge_kernel<64, false><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off); }
-    else         { if (dtype) fa_merge_kernel<128, true><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off);
-                   else fa_merge_kernel<128, false><<<(int)blocks, 256, 0, st>>>(oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off); }
+    if (D == 64) { if (dtype) launch_pdl(fa_merge_kernel<64, true>, (int)blocks, 256, 0, st, oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off);
+                   else launch_pdl(fa_merge_kernel<64, false>, (int)blocks, 256, 0, st, oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off); }
+    else         { if (dtype) launch_pdl(fa_merge_kernel<128, true>, (int)blocks, 256, 0, st, oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off);
+                   else launch_pdl(fa_merge_kernel<128, false>, (int)blocks, 256, 0, st, oa, lse_acc, op, lse_part, rows, Sq, Sq_acc, q_off); }
     return (int)cudaGetLastError();
 }
 

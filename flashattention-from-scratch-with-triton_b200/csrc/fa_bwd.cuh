@@ -201,6 +201,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
     // D=64 leaves 128 TMEM columns free: S^T is double-buffered there, so S^T(i+1) is ready before the math
     // of tile i ends (the S -> P -> dV -> S chain otherwise dominates when the MMAs are short).
     constexpr bool kDoubleS = (D == 64);
@@ -617,6 +618,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
     constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDS = 256 + D;   // dS buffers: kColDS + 64*(g&1)
 
     // item -> (bh, q tile, number of kv tiles); descending q tile = heavy first under causal (:219 truncation)
@@ -855,14 +857,15 @@ int launch_bwd_td(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMa
     if (parts & 2) {
         const int items = p.BH * p.n_qtiles;
         const int grid = FA_BWD_PERSISTENT ? (items < p.sms ? items : p.sms) : items;
-        fa_bwd_dq_kernel<D, kBf16, kDropout><<<grid, kBwdThreads, DqCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = launch_pdl(fa_bwd_dq_kernel<D, kBf16, kDropout>, grid, kBwdThreads, DqCfg<D>::kSmemBytes, st, mq, mk, mv, mdo, mdq, p);
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
     if (parts & 4) {
         const int items = (p.BH / p.G) * p.n_ktiles;
         const int grid = FA_BWD_PERSISTENT ? (items < p.sms ? items : p.sms) : items;
-        fa_bwd_dkv_kernel<D, kBf16, kDropout><<<grid, kBwdThreads, DkvCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
+        cudaError_t e = launch_pdl(fa_bwd_dkv_kernel<D, kBf16, kDropout>, grid, kBwdThreads, DkvCfg<D>::kSmemBytes, st, mq, mk, mv, mdo, mdk, mdv, p);
+        if (e != cudaSuccess) return (int)e;
     }
     return (int)cudaGetLastError();
 }

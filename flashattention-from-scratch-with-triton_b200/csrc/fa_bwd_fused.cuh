@@ -137,6 +137,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
     // dQ partial (fp32, q lanes) and P^T (16-bit, kv lanes) take turns in ONE region: dQ(i-1) is drained right before P^T(i)
     // is written, dV(i) has consumed P^T(i) before the in-order MMA pipe reaches dQ(i).  The 64 columns this saves hold K and V
     // (16-bit, kv lanes) as the A operands of the two score MMAs: 32 KB less shared-memory operand traffic per tile — the
@@ -540,6 +541,7 @@ __global__ void __launch_bounds__(256) fa_dq_convert_kernel(const float4* __rest
     constexpr int U = 4;
     const int sub = threadIdx.x % TPR;
     const long long stride = (long long)gridDim.x * RPB;
+    pdl_wait();
     for (long long row0 = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row0 < rows; row0 += stride * U) {
         float4 a[U], b[U];
         #pragma unroll
@@ -574,16 +576,17 @@ int launch_bwd_fused_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
     }
     const int items = (p.BH / p.G) * p.n_ktiles;
     const int grid = items < p.sms ? items : p.sms;
-    if (parts & 8) fa_bwd_fused_kernel<D, kBf16><<<grid, kBwdThreads, FusedCfg<D>::kSmemBytes, st>>>(mq, mk, mv, mdo, mdk, mdv, macc, p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    if (parts & 8) e = launch_pdl(fa_bwd_fused_kernel<D, kBf16>, grid, kBwdThreads, FusedCfg<D>::kSmemBytes, st, mq, mk, mv, mdo, mdk, mdv, macc, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess || !(parts & 16)) return (int)e;
     const long long rows = (long long)p.BH * p.Sq;
     const int rpb = 256 / (D / 8) * 4;
     long long blocks = (rows + rpb - 1) / rpb;
     const long long cap = (long long)p.sms * 8;
     if (blocks > cap) blocks = cap;
-    fa_dq_convert_kernel<D, kBf16><<<(int)blocks, 256, 0, st>>>((const float4*)acc, (uint4*)dq, rows, p.H, p.Sq, s_dq, p.scale);
-    return (int)cudaGetLastError();
+    e = launch_pdl(fa_dq_convert_kernel<D, kBf16>, (int)blocks, 256, 0, st, (const float4*)acc, (uint4*)dq, rows, p.H, p.Sq, s_dq, p.scale);
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 }  // namespace fa

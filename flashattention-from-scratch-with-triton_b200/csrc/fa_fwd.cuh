@@ -156,6 +156,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
 
     if (warp == 11) {
         reg_dealloc<FwdRegs<D>::kOther>();     // idle warp (register donor)

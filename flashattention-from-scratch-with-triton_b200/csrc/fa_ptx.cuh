@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <utility>
 
 namespace fa {
 
@@ -434,6 +435,25 @@ __device__ __forceinline__ void item_to_head_tile(int item, int n_heads, int n_t
 // word 0 has returned by then, and the next user of the slot is a later launch.
 __device__ __forceinline__ void sched_retire(unsigned int* sched) {
     if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
+}
+
+// Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-serialization attribute
+// (launch_pdl) and executes pdl_wait() before its first global-memory access: the launch and the prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) overlap the tail of the previous kernel in the stream; pdl_wait returns once that kernel has
+// completed and its writes are visible.  A short step (C2: fwd, delta, fused, convert = 0.2 ms) otherwise pays a launch gap per boundary.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef FA_PDL
+#define FA_PDL 1
+#endif
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = FA_PDL ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it)

@@ -1,7 +1,4 @@
 timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | cut -c1-300
-timeout 300 python bench.py > gpurun_out/c58_bench.json 2> gpurun_out/c58_bench.err; tail -2 gpurun_out/c58_bench.err; python - <<'PY'
-import json
-d=json.load(open('gpurun_out/c58_bench.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks']['sm_mhz'])
-print({k:(round(v['ms'],4), round(v['achieved'],1)) for k,v in d['kernels'].items()})
-PY
+for v in pdl nopdl pdl nopdl; do if [ $v = pdl ]; then unset FA_SM100_LIB; else export FA_SM100_LIB=$PWD/build/variants/libfa_sm100_$v.so; fi; timeout 200 python bench.py --no-extras 2>/dev/null | python -c "
+import json,sys; d=json.load(sys.stdin); print('$v C2', round(d['value'],1), round(d['ms_per_step'],4))"; timeout 200 python bench.py --no-extras --workload C3 2>/dev/null | python -c "
+import json,sys; d=json.load(sys.stdin); print('$v C3', round(d['value'],1), round(d['ms_per_step'],4))"; done
