@@ -61,11 +61,13 @@ template <int D> struct FwdRegs { static constexpr int kSoftmax = 208, kOther = 
 static_assert(2 * FwdRegs<64>::kSoftmax + FwdRegs<64>::kOther <= 504 && 2 * FwdRegs<128>::kSoftmax + FwdRegs<128>::kOther <= 504, "register pool");
 // Of every FA_FWD_POLY_DEN pairs of exponentials, FA_FWD_POLY_NUM are evaluated on the FMA pipe (ex2_poly2),
 // the rest on the MUFU unit: the exp loop is XU-saturated (profiles/), the polynomial shifts load to FFMA2.
+// Measured (profiles/r01_ab_fwd_poly_recheck.txt): 1/4 and more is slower (the loop turns issue-bound), 1/8 is -3 % on long D=64
+// sequences and neutral elsewhere.
 #ifndef FA_FWD_POLY_NUM
-#define FA_FWD_POLY_NUM 0
+#define FA_FWD_POLY_NUM 1
 #endif
 #ifndef FA_FWD_POLY_DEN
-#define FA_FWD_POLY_DEN 4
+#define FA_FWD_POLY_DEN 8
 #endif
 // The two softmax warpgroups do identical work and would otherwise run in lockstep, hitting the MUFU unit
 // at the same time and leaving it idle at the same time.  Turn-taking around the exp loop (named barriers

@@ -62,6 +62,8 @@ def as_kernel_layout(t: torch.Tensor) -> torch.Tensor:
     """The reference always calls .contiguous() (code/My_FlashAttention_optimized.py:138-140, :156); here a
     strided view (e.g. a [B,H,S,D] transpose of a [B,S,H,D] projection output) is used in place, and only
     layouts the TMA cannot express are copied."""
+    if t.is_contiguous() and t.data_ptr() % 16 == 0 and t.ndim == 4:      # the common case, checked cheaply (host time per
+        return t                                                          # step is comparable to a short step's GPU time)
     return t if tma_compatible(t) else t.contiguous()
 
 
@@ -142,7 +144,7 @@ def flash_attention_forward(Q, K, V, is_causal, sm_scale=None, ranges=None, drop
     B, H, S_q, D = Q.shape
     _, _, S_k, _ = K.shape
     O = torch.empty_like(Q)                               # contiguous Q -> contiguous O (reference :23); else Q's layout
-    if not tma_compatible(O):
+    if not O.is_contiguous() and not tma_compatible(O):
         O = torch.empty((B, H, S_q, D), dtype=Q.dtype, device=Q.device)
     LSE = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
     st = _strides(Q, K, V, O)
@@ -222,7 +224,7 @@ def flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_ca
 
 def _empty_like_kernel(t):
     e = torch.empty_like(t)
-    return e if tma_compatible(e) else torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    return e if e.is_contiguous() or tma_compatible(e) else torch.empty(t.shape, dtype=t.dtype, device=t.device)
 
 
 def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None, ranges=None, dropout_p=0.0, dropout_seed=0):
