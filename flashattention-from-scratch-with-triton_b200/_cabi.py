@@ -24,6 +24,7 @@ SYMBOLS = {
     "fa_sm100_fwd_opt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "fa_sm100_bwd_opt": (_i, [_vp] * 10 + [_i] * 8 + [_f, _vp, _vp, _vp, _i]),
     "fa_sm100_bwd_fused": (_i, [_vp] * 11 + [_i] * 8 + [_f, _vp, _vp, _i]),
+    "fa_sm100_bwd_fused_opt": (_i, [_vp] * 11 + [_i] * 8 + [_f, _vp, _vp, _vp, _i]),
     "fa_sm100_bwd_fused_workspace": (ctypes.c_size_t, [_i, _i, _i, _i]),
     "fa_sm100_bwd_parts": (_i, [_vp] * 10 + [_i] * 7 + [_f, _vp, _i]),
     "fa_sm100_delta": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -156,13 +156,13 @@ template <typename K> cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-template <int D, bool kBf16, bool kRanges>
+template <int D, bool kBf16, bool kRanges, bool kDropout>
 int launch_fwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
                  const FwdParams& p, int grid, cudaStream_t st) {
     static std::once_flag once; static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = set_smem(fa_fwd_kernel<D, kBf16, kRanges>, FwdCfg<D>::kSmemBytes); });
+    std::call_once(once, [] { attr_err = set_smem(fa_fwd_kernel<D, kBf16, kRanges, kDropout>, FwdCfg<D>::kSmemBytes); });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(fwd smem)");
-    cudaError_t e = launch_pdl(fa_fwd_kernel<D, kBf16, kRanges>, grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st, mq, mk, mv, mo, p);
+    cudaError_t e = launch_pdl(fa_fwd_kernel<D, kBf16, kRanges, kDropout>, grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st, mq, mk, mv, mo, p);
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd_kernel launch");
@@ -170,8 +170,10 @@ int launch_fwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
 template <int D, bool kBf16>
 int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
                const FwdParams& p, int grid, cudaStream_t st) {
-    return (p.row_lo || p.drop.thresh) ? launch_fwd_t<D, kBf16, true>(mq, mk, mv, mo, p, grid, st)
-                                       : launch_fwd_t<D, kBf16, false>(mq, mk, mv, mo, p, grid, st);
+    if (p.drop.thresh) return p.row_lo ? launch_fwd_t<D, kBf16, true, true>(mq, mk, mv, mo, p, grid, st)
+                                       : launch_fwd_t<D, kBf16, false, true>(mq, mk, mv, mo, p, grid, st);
+    return p.row_lo ? launch_fwd_t<D, kBf16, true, false>(mq, mk, mv, mo, p, grid, st)
+                    : launch_fwd_t<D, kBf16, false, false>(mq, mk, mv, mo, p, grid, st);
 }
 
 }  // namespace
@@ -375,6 +377,17 @@ int fa_sm100_bwd_fused(const void* q, const void* k, const void* v, const void* 
                        const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_acc,
                        int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                        const long long* strides, void* stream, int parts) {
+    return fa_sm100_bwd_fused_opt(q, k, v, o, dout, lse, dq, dk, dv, delta, dq_acc, B, H, Hk, Sq, Sk, D, dtype, causal, sm_scale,
+                                  strides, nullptr, stream, parts);
+}
+
+int fa_sm100_bwd_fused_opt(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                           const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_acc,
+                           int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
+                           const long long* strides, const fa_sm100_options* opt, void* stream, int parts) {
+    DropoutParams drop; if (int rc = make_dropout(opt, &drop)) return rc;
+    const int* col_lo = opt ? opt->col_lo : nullptr; const int* col_hi = opt ? opt->col_hi : nullptr;
+    if (!col_lo != !col_hi) return fail(FA_ERR_NULL, "col_lo and col_hi must be given together");
     if (parts == 0) parts = FA_BWD_DELTA | FA_BWD_FUSED | FA_BWD_CONVERT;
     if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta || !dq_acc) return fail(FA_ERR_NULL, "null tensor pointer");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
@@ -412,8 +425,8 @@ int fa_sm100_bwd_fused(const void* q, const void* k, const void* v, const void* 
     p.scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse; p.delta = delta;
-    p.row_lo = p.row_hi = p.col_lo = p.col_hi = nullptr;
-    p.drop.seed0 = p.drop.seed1 = p.drop.thresh = 0; p.drop.scale = 1.f;
+    p.row_lo = p.row_hi = nullptr; p.col_lo = col_lo; p.col_hi = col_hi;     // the fused kernel sees the mask from the key side only
+    p.drop = drop;
     p.n_qtiles = (Sq + 127) / 128; p.n_ktiles = (Sk + 127) / 128;
     p.sms = dev->sms;
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);

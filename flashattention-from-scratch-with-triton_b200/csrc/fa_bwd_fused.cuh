@@ -83,7 +83,10 @@ __device__ __forceinline__ void issue_scores_ts(uint32_t d_tmem, uint32_t a_tmem
         umma_ts_e(d_tmem, a_tmem + k * 8, make_smem_desc(b_addr + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024), idesc, k > 0);
 }
 
-template <int D, bool kBf16>
+// kExt: 0 = the plain kernel; 1 = range masks (BwdParams::col_lo/col_hi, if set); 2 = dropout (and range masks, if set) — exactly
+// as in the dK/dV kernel of fa_bwd.cuh.  Separate instantiations: the plain kernel is unchanged and the range-masked one does not
+// carry the dropout generator.
+template <int D, bool kBf16, int kExt = 0>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
@@ -148,10 +151,18 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 
     // item -> (batch*Hk + kv head, kv tile, first q tile, iterations); with GQA the item walks the q tiles of every
     // query head of the group (dK/dV reduce over the group in TMEM)
-    auto decode = [&](int item, int& bh, int& jt, int& i_start, int& n_it) {
+    auto decode = [&](int item, int& bh, int& jt, int& i_start, int& i_end, int& n_it) {
         item_to_head_tile(item, p.BH / p.G, p.n_ktiles, p.hc_dkv, bh, jt);
         i_start = p.causal ? jt : 0;
-        n_it = max(p.n_qtiles - i_start, 0) * p.G;
+        i_end = p.n_qtiles;
+        if constexpr (kExt) {
+            if (p.col_lo) {                                // q tiles [first query of the first kv row, last query of the last kv row)
+                const size_t cb = (size_t)(bh / p.Hk) * p.Sk;
+                i_start = max(i_start, __ldg(p.col_lo + cb + min(jt * 128, p.Sk - 1)) >> 7);
+                i_end = min(i_end, ((min(__ldg(p.col_hi + cb + min(jt * 128 + 127, p.Sk - 1)), p.Sq) - 1) >> 7) + 1);
+            }
+        }
+        n_it = max(i_end - i_start, 0) * p.G;
     };
     auto next_item = [&](uint32_t ix) -> int {                 // whole warp
         const uint32_t slot = ix & 1;
@@ -169,12 +180,12 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
-            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
             int qtile = i_start, hq = (bh % p.Hk) * p.G;
             const int bq = bh / p.Hk;
             for (int it = 0; it < n_it; ++it, ++nd) {
                 const int q0 = qtile * 128, bhq = bq * p.H + hq;
-                if (++qtile == p.n_qtiles) { qtile = i_start; ++hq; }
+                if (++qtile == i_end) { qtile = i_start; ++hq; }
                 mbar_wait(dqs_full, nd & 1, 650);
                 if (lane_id() == 0) {
                     if (!(FA_FUSED_SKIP & 1)) {
@@ -198,14 +209,14 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
-            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
             int s_qtile = i_start;
             size_t s_row0 = ((size_t)(bh / p.Hk) * p.H + (size_t)(bh % p.Hk) * p.G) * p.Sq;
             const bool vec_ok = (p.Sq & 3) == 0;
             auto fetch = [&](float4& nl, float4& dl) {
                 const int q0 = s_qtile * 128 + lane * 4;
                 const size_t off = s_row0 + q0;
-                if (++s_qtile == p.n_qtiles) { s_qtile = i_start; s_row0 += p.Sq; }
+                if (++s_qtile == i_end) { s_qtile = i_start; s_row0 += p.Sq; }
                 float l[4];
                 if (vec_ok && q0 + 4 <= p.Sq) {
                     const float4 lv = __ldg(reinterpret_cast<const float4*>(p.lse + off));
@@ -260,7 +271,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             sched_item[slot] = item;
             mbar_arrive_e(&sched_full[slot]);
             if (item >= n_items) break;
-            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
             const uint32_t kb = ix & 1;                   // K/V buffer of this item; its previous user was item ix - 2
             uint8_t* sK = sKV + kb * 2 * C::kTileBytes;
             uint8_t* sV = sK + C::kTileBytes;
@@ -279,7 +290,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                     uint8_t* sQi = sStage + st * C::kStageBytes;
                     uint8_t* sdOi = sQi + C::kTileBytes;
                     const int q0 = l_qtile * 128, hcur = hq;
-                    if (++l_qtile == p.n_qtiles) { l_qtile = i_start; ++hq; }
+                    if (++l_qtile == i_end) { l_qtile = i_start; ++hq; }
                     mbar_wait(&stage_empty[st], ((git / C::kStages) & 1) ^ 1, 610);
                     mbar_arrive_expect_tx_e(&q_full[st], C::kTileBytes);
                     tma_load_4d_e(sQi, &mapQ, &q_full[st], 0, q0, hcur, bq);
@@ -303,7 +314,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
-            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
             auto qfull = [&](uint32_t g) { mbar_wait(&q_full[g % C::kStages], (g / C::kStages) & 1, 621); };
             auto dofull = [&](uint32_t g) { mbar_wait(&do_full[g % C::kStages], (g / C::kStages) & 1, 623); };
             auto stage_addr = [&](uint32_t g) { return aSt + (g % C::kStages) * C::kStageBytes; };
@@ -413,15 +424,24 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         if (item < n_items) copy_kv(0);
         for (uint32_t ix = 0;; ++ix) {
             if (item >= n_items) break;
-            int bh, jt, i_start, n_it; decode(item, bh, jt, i_start, n_it);
+            int bh, jt, i_start, i_end, n_it; decode(item, bh, jt, i_start, i_end, n_it);
             const int kv_g = jt * 128 + r;
+            int q_lo = p.causal ? kv_g : 0, q_hi = p.Sq;  // queries that see my kv row
+            if constexpr (kExt) {
+                if (p.col_lo) {
+                    const size_t ci = (size_t)(bh / p.Hk) * p.Sk + min(kv_g, p.Sk - 1);
+                    q_lo = max(q_lo, __ldg(p.col_lo + ci)); q_hi = min(q_hi, __ldg(p.col_hi + ci));
+                }
+            }
             int qtile = i_start;
+            uint32_t bhq = (uint32_t)((bh / p.Hk) * p.H + (bh % p.Hk) * p.G);   // batch*H + query head of the current iteration
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it;
                 const uint32_t ss = g % C::kStatStages;
                 const uint32_t stat = smem_u32(sStat) + ss * 1024 + h * 256;
                 const int q0 = qtile * 128 + h * 64;                 // global query index of my column 0
-                if (++qtile == p.n_qtiles) qtile = i_start;
+                const uint32_t bhq_it = bhq;
+                if (++qtile == i_end) { qtile = i_start; ++bhq; }
                 mbar_wait(&stat_full[ss], (g / C::kStatStages) & 1, 630);
                 mbar_wait(s_full, g & 1, 631);
                 tc_fence_after();
@@ -454,17 +474,34 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                     }
                     if (FA_FUSED_STAGGER) named_bar_arrive(4 - h, 256);
                 }
-                if (p.causal && q0 < kv_g) {                 // tile straddles the diagonal: keep q >= kv only
-                    const int cmin = kv_g - q0;
+                if (kExt ? (q0 < q_lo || q0 + 64 > q_hi) : (p.causal && q0 < kv_g)) {   // tile straddles the diagonal / a range end
+                    const int cmin = q_lo - q0, cmax = kExt ? q_hi - 1 - q0 : 63;
                     #pragma unroll
-                    for (int c = 0; c < 64; ++c) if (c < cmin) pv[c] = 0.f;
+                    for (int c = 0; c < 64; ++c) if (c < cmin || c > cmax) pv[c] = 0.f;
                 }
+                uint64_t keep = ~0ull;                       // dropout keep bit per column (query) of my kv row
+                constexpr bool drop = (kExt == 2);
+                if constexpr (drop) {
+                    keep = 0ull;
+                    #pragma unroll
+                    for (int c = 0; c < 64; ++c) {
+                        const uint32_t w = dropout_word(dropout_row_key(p.drop.seed0, bhq_it, (uint32_t)(q0 + c)), p.drop.seed1, (uint32_t)kv_g >> 2);
+                        keep |= (uint64_t)dropout_keep(w, (uint32_t)kv_g, p.drop.thresh) << c;
+                    }
+                }
+                const float dscale = drop ? p.drop.scale : 1.f;
                 if (it > 0) drain_dq(g - 1);                 // frees the shared TMEM region (its MMAs finished during the exp)
                 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     uint32_t pk[16];
                     #pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = pack2<kBf16>(pv[q * 32 + 2 * i], pv[q * 32 + 2 * i + 1]);
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = q * 32 + 2 * i;
+                        if constexpr (drop)                    // dV sees the dropped-out, rescaled P^T; pv keeps P for dS
+                            pk[i] = pack2<kBf16>(((keep >> c) & 1) ? pv[c] * dscale : 0.f, ((keep >> (c + 1)) & 1) ? pv[c + 1] * dscale : 0.f);
+                        else
+                            pk[i] = pack2<kBf16>(pv[c], pv[c + 1]);
+                    }
                     tmem_st16(tP + q * 16, pk);
                 }
                 tc_wait_st(); tc_fence_before();
@@ -484,10 +521,14 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                             const int c = q * 32 + 2 * i;
                             const float4 dl = lds128(stat + 512 + c * 4);
                             float d0, d1, d2, d3;        // dS = P o (dP - delta), packed: FADD2 + FMUL2
-                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]),
-                                            fadd2(pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), pack_f2(dl.x, dl.y))), d0, d1);
-                            unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]),
-                                            fadd2(pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]), pack_f2(dl.z, dl.w))), d2, d3);
+                            uint64_t dpa = pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), dpb = pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]);
+                            if constexpr (drop) {
+                                float e0, e1, e2, e3; unpack_f2(dpa, e0, e1); unpack_f2(dpb, e2, e3);
+                                dpa = pack_f2(((keep >> c) & 1) ? e0 * dscale : 0.f, ((keep >> (c + 1)) & 1) ? e1 * dscale : 0.f);
+                                dpb = pack_f2(((keep >> (c + 2)) & 1) ? e2 * dscale : 0.f, ((keep >> (c + 3)) & 1) ? e3 * dscale : 0.f);
+                            }
+                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), fadd2(dpa, pack_f2(dl.x, dl.y))), d0, d1);
+                            unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]), fadd2(dpb, pack_f2(dl.z, dl.w))), d2, d3);
                             pk[i] = pack2<kBf16>(d0, d1); pk[i + 1] = pack2<kBf16>(d2, d3);
                         }
                         tmem_st16(tDPT + q * 16, pk);                        // A operand of dK (in place of dP^T)
@@ -563,21 +604,21 @@ __global__ void __launch_bounds__(256) fa_dq_convert_kernel(const float4* __rest
     }
 }
 
-template <bool kBf16>
-int launch_bwd_fused_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
-                       const CUtensorMap& mdk, const CUtensorMap& mdv, const CUtensorMap& macc, const BwdParams& p,
-                       const float* acc, void* dq, RowStrides s_dq, cudaStream_t st, int parts) {
+template <bool kBf16, int kExt>
+int launch_bwd_fused_te(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
+                        const CUtensorMap& mdk, const CUtensorMap& mdv, const CUtensorMap& macc, const BwdParams& p,
+                        const float* acc, void* dq, RowStrides s_dq, cudaStream_t st, int parts) {
     constexpr int D = 64;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(fa_bwd_fused_kernel<D, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<D>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(fa_bwd_fused_kernel<D, kBf16, kExt>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
     const int items = (p.BH / p.G) * p.n_ktiles;
     const int grid = items < p.sms ? items : p.sms;
     cudaError_t e = cudaSuccess;
-    if (parts & 8) e = launch_pdl(fa_bwd_fused_kernel<D, kBf16>, grid, kBwdThreads, FusedCfg<D>::kSmemBytes, st, mq, mk, mv, mdo, mdk, mdv, macc, p);
+    if (parts & 8) e = launch_pdl(fa_bwd_fused_kernel<D, kBf16, kExt>, grid, kBwdThreads, FusedCfg<D>::kSmemBytes, st, mq, mk, mv, mdo, mdk, mdv, macc, p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess || !(parts & 16)) return (int)e;
     const long long rows = (long long)p.BH * p.Sq;
@@ -587,6 +628,15 @@ int launch_bwd_fused_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
     if (blocks > cap) blocks = cap;
     e = launch_pdl(fa_dq_convert_kernel<D, kBf16>, (int)blocks, 256, 0, st, (const float4*)acc, (uint4*)dq, rows, p.H, p.Sq, s_dq, p.scale);
     return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
+}
+
+template <bool kBf16>
+int launch_bwd_fused_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
+                       const CUtensorMap& mdk, const CUtensorMap& mdv, const CUtensorMap& macc, const BwdParams& p,
+                       const float* acc, void* dq, RowStrides s_dq, cudaStream_t st, int parts) {
+    if (p.drop.thresh) return launch_bwd_fused_te<kBf16, 2>(mq, mk, mv, mdo, mdk, mdv, macc, p, acc, dq, s_dq, st, parts);
+    return p.col_lo ? launch_bwd_fused_te<kBf16, 1>(mq, mk, mv, mdo, mdk, mdv, macc, p, acc, dq, s_dq, st, parts)
+                    : launch_bwd_fused_te<kBf16, 0>(mq, mk, mv, mdo, mdk, mdv, macc, p, acc, dq, s_dq, st, parts);
 }
 
 }  // namespace fa

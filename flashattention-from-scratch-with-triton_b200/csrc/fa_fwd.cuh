@@ -107,10 +107,11 @@ __device__ __forceinline__ int fwd_item_iters(const int* row_lo, const int* row_
     return max(((hi - 1) >> 7) - jb + 1, 0);
 }
 
-// kRanges: the extended instantiation — per-row key ranges (if the pointers are set) and dropout (if drop.thresh > 0).  The plain
-// operator keeps its own instantiation and register budget: the softmax loop sits at the 208-register ceiling and three more
-// live values spill.
-template <int D, bool kBf16, bool kRanges = false>
+// kRanges / kDropout: separate instantiations for the per-row key ranges and for dropout.  The plain operator keeps its own code and
+// register budget (the softmax loop sits at the 208-register ceiling and three more live values spill), and the range-masked one
+// must not carry the dropout generator: as a run-time branch inside the exp loop it was if-converted and made the packed
+// variable-length forward 2.2x slower with dropout off.
+template <int D, bool kBf16, bool kRanges = false, bool kDropout = false>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapO,
@@ -423,14 +424,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             }
             const int row_g = q0 + t * 128 + r;
             int k_lo = 0, k_hi = p.Sk;                    // keys this row may see (before the causal clip)
-            uint32_t drop_key = 0;
             if constexpr (kRanges) {
-                if (p.row_lo) {
-                    const size_t ri = (size_t)(bh / p.H) * p.Sq + min(row_g, p.Sq - 1);
-                    k_lo = __ldg(p.row_lo + ri); k_hi = min(__ldg(p.row_hi + ri), p.Sk);
-                }
-                drop_key = dropout_row_key(p.drop.seed0, (uint32_t)bh, (uint32_t)row_g);
+                const size_t ri = (size_t)(bh / p.H) * p.Sq + min(row_g, p.Sq - 1);
+                k_lo = __ldg(p.row_lo + ri); k_hi = min(__ldg(p.row_hi + ri), p.Sk);
             }
+            const uint32_t drop_key = kDropout ? dropout_row_key(p.drop.seed0, (uint32_t)bh, (uint32_t)row_g) : 0u;
             float m = -INFINITY, l = 0.f;
             for (int j = 0; j < nt; ++j) {
                 mbar_wait(&s_full[t], ph_s, 301); ph_s ^= 1;
@@ -503,13 +501,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                             p0 = ex2_approx(x0); p1 = ex2_approx(x1);
                         }
                         if (i & 1) lB = fadd2(lB, pack_f2(p0, p1)); else lA = fadd2(lA, pack_f2(p0, p1));   // l: before dropout
-                        if constexpr (kRanges) {
-                            if (p.drop.thresh) {               // O accumulates the dropped-out, rescaled P; LSE / l do not
-                                const uint32_t kcol = (uint32_t)(kbase + q * 32 + 2 * i);
-                                const uint32_t w = dropout_word(drop_key, p.drop.seed1, kcol >> 2);
-                                p0 = dropout_keep(w, kcol, p.drop.thresh) ? p0 * p.drop.scale : 0.f;
-                                p1 = dropout_keep(w, kcol + 1, p.drop.thresh) ? p1 * p.drop.scale : 0.f;
-                            }
+                        if constexpr (kDropout) {              // O accumulates the dropped-out, rescaled P; LSE / l do not
+                            const uint32_t kcol = (uint32_t)(kbase + q * 32 + 2 * i);
+                            const uint32_t w = dropout_word(drop_key, p.drop.seed1, kcol >> 2);
+                            p0 = dropout_keep(w, kcol, p.drop.thresh) ? p0 * p.drop.scale : 0.f;
+                            p1 = dropout_keep(w, kcol + 1, p.drop.thresh) ? p1 * p.drop.scale : 0.f;
                         }
                         pk[i] = pack2<kBf16>(p0, p1);
                     }

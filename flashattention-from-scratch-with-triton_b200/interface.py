@@ -205,7 +205,8 @@ def fused_backward_supported(Q) -> bool:
 BWD_FUSED, BWD_CONVERT = 8, 16
 
 
-def flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale=None, dq_acc=None, parts=0):
+def flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale=None, dq_acc=None, parts=0,
+                                   ranges=None, dropout_p=0.0, dropout_seed=0):
     """delta -> fused dK/dV/dQ kernel -> dQ conversion (head dim 64).  dq_acc: optional fp32 [B,H,S_q,D] workspace."""
     lib = _cabi.load()
     B, H, S_q, D = Q.shape
@@ -215,11 +216,12 @@ def flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_ca
     assert dq_acc.dtype == torch.float32 and dq_acc.is_contiguous() and dq_acc.numel() == B * H * S_q * D
     st = _strides(Q, K, V, O, dO, dQ, dK, dV)
     with _on_device(Q):
-        rc = lib.fa_sm100_bwd_fused(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
-                                    LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
-                                    dq_acc.data_ptr(), B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
-                                    float(sm_scale) if sm_scale is not None else 0.0, st, _stream(Q), int(parts))
-    _cabi.check("fa_sm100_bwd_fused", rc)
+        rc = lib.fa_sm100_bwd_fused_opt(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
+                                        LSE.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), delta.data_ptr(),
+                                        dq_acc.data_ptr(), B, H, K.shape[1], S_q, S_k, D, _DT[Q.dtype], int(bool(is_causal)),
+                                        float(sm_scale) if sm_scale is not None else 0.0, st,
+                                        _options(ranges, dropout_p, dropout_seed, backward=True), _stream(Q), int(parts))
+    _cabi.check("fa_sm100_bwd_fused_opt", rc)
 
 
 def _empty_like_kernel(t):
@@ -232,9 +234,10 @@ def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None, rang
     B, H, S_q, D = Q.shape
     dQ, dK, dV = _empty_like_kernel(Q), _empty_like_kernel(K), _empty_like_kernel(V)      # reference :71-73
     delta = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
-    if fused_backward_supported(Q) and not _deterministic and ranges is None and not dropout_p:
-        flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale)
-    else:                                                  # range masks and dropout run on the two-kernel path
+    if fused_backward_supported(Q) and not _deterministic:
+        flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale, None, 0, ranges, dropout_p,
+                                       dropout_seed)
+    else:
         flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, BWD_DELTA | BWD_DQ | BWD_DKV, sm_scale,
                                        ranges, dropout_p, dropout_seed)
     return dQ, dK, dV

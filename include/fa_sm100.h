@@ -79,7 +79,7 @@ int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void
  * non-decreasing along the sequence (the kernels derive their tile ranges from the first and last row of a tile), and must
  * describe the same mask; every query row must see at least one key.  Tiles outside the ranges are skipped, not masked:
  * packing N sequences costs the sum of their squares.  Packed [total,H,D] tensors are passed as B = 1, Sq = Sk = total with
- * strides {0, D, H*D}.  NULL ranges = the plain operator.  The backward is the deterministic two-kernel path. */
+ * strides {0, D, H*D}.  NULL ranges = the plain operator. */
 int fa_sm100_fwd_ranges(const void* q, const void* k, const void* v, void* o, float* lse,
                         int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                         const long long* strides, const int* row_lo, const int* row_hi, void* stream);
@@ -104,7 +104,7 @@ int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* 
  * "next step" (Phase_6.md:54-114).  Each attention probability is kept with probability 1 - p and scaled by 1 / (1 - p); p is
  * quantised to thresh / 256 (one random byte per element).  The keep mask is a pure function of (dropout_seed, batch * H + head,
  * query row, key column) — mix32 / dropout_word in csrc/fa_ptx.cuh; the tests pin it with a numpy restatement — so the backward
- * regenerates it from the same seed; LSE is that of the undropped softmax.  The backward with dropout is the two-kernel path. */
+ * regenerates it from the same seed; LSE is that of the undropped softmax. */
 typedef struct fa_sm100_options {
     const int* row_lo; const int* row_hi;       /* [B,Sq] or NULL */
     const int* col_lo; const int* col_hi;       /* [B,Sk] or NULL (backward only) */
@@ -134,6 +134,12 @@ int fa_sm100_bwd_fused(const void* q, const void* k, const void* v, const void* 
                        const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_acc,
                        int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal,
                        float sm_scale, const long long* strides, void* stream, int parts);
+
+/* The fused backward with options: range masks (col_lo / col_hi — it only needs the key-side view) and dropout. */
+int fa_sm100_bwd_fused_opt(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                           const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_acc,
+                           int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal,
+                           float sm_scale, const long long* strides, const fa_sm100_options* opt, void* stream, int parts);
 
 /* delta = rowsum(dout * o) alone (the preprocess step of the backward; kernel :210-211). */
 int fa_sm100_delta(const void* o, const void* dout, float* delta,
