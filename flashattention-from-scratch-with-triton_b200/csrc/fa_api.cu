@@ -87,7 +87,8 @@ bool strides_ok(RowStrides& st, int B, int H, int S, int D) {
     return st.b > 0 && st.h > 0 && st.r >= D && (st.b % 8 == 0) && (st.h % 8 == 0) && (st.r % 8 == 0);
 }
 
-struct DeviceInfo { int sms = 0; int cc_major = 0; unsigned int* sched_ring = nullptr; };
+// `ready` publishes the other fields (release / acquire): concurrent first calls on one device are safe
+struct DeviceInfo { int sms = 0; int cc_major = 0; unsigned int* sched_ring = nullptr; std::atomic<int> ready{0}; };
 constexpr int kMaxDevices = 64;
 constexpr int kSchedRing = 1024;
 __device__ unsigned int g_sched_ring[kSchedRing];
@@ -105,9 +106,9 @@ int device_info(DeviceInfo** out) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
     if (dev < 0 || dev >= kMaxDevices) return fail(FA_ERR_DEVICE, "device ordinal %d out of range", dev);
     DeviceInfo& d = g_dev[dev];
-    if (d.sms == 0) {
+    if (!d.ready.load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lk(g_dev_mu);
-        if (d.sms == 0) {
+        if (!d.ready.load(std::memory_order_relaxed)) {
             int sms = 0, major = 0;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
@@ -115,6 +116,7 @@ int device_info(DeviceInfo** out) {
             e = cudaGetSymbolAddress(&ring, g_sched_ring);
             if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(sched ring) — was the library built for sm_100a?");
             d.cc_major = major; d.sched_ring = (unsigned int*)ring; d.sms = sms;
+            d.ready.store(1, std::memory_order_release);
         }
     }
     if (d.cc_major != 10) return fail(FA_ERR_DEVICE, "libfa_sm100 needs compute capability 10.x, device has %d.x", d.cc_major);
