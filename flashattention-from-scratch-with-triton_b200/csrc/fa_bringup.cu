@@ -69,6 +69,9 @@ struct GemmParams {
     int bf16;
     int store_mode;                 // 0: D fp32 to global via registers; 1: also TMA-store a 16-bit copy;
                                     // 2: also reduce-add the fp32 tile twice into R_out through mapRed (TMA .add)
+    // extra K = 16 step from two compact NO-SWIZZLE tiles written by the threads: A' = [128 x 16] with ones in columns 0-2,
+    // B' = [n x 16] with a 3-way bf16 split of x[col] in columns 0-2  =>  D[m][col] += x[col]  (statistics through the MMA)
+    int extra_kstep; uint32_t x_lbo, x_sbo;
 };
 
 // D[128 x n] = A[128 x K] * B   (B either [n x K] K-major or [K x n] MN-major, per descriptors)
@@ -119,6 +122,24 @@ bringup_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         tc_wait_st();
         tc_fence_before();
     }
+    uint8_t* sXA = smem + 131072 - 8192;    // compact tiles of the extra k-step (inside the staging area, unused by these tests)
+    uint8_t* sXB = sXA + 4096;
+    if (p.extra_kstep) {
+        // thread r writes row r of both tiles: core matrix (r/8, k-chunk j) at (r/8)*256 + j*128, row r%8 at +16 bytes each
+        const uint32_t one = 0x3f80u;                               // bf16 1.0
+        const float x = 0.37f * (float)tid - 11.5f + 1e-3f * (float)(tid * tid % 97);
+        const __nv_bfloat16 hi = __float2bfloat16(x), mid = __float2bfloat16(x - __bfloat162float(hi));
+        const __nv_bfloat16 lo = __float2bfloat16(x - __bfloat162float(hi) - __bfloat162float(mid));
+        uint16_t h16, m16, l16; memcpy(&h16, &hi, 2); memcpy(&m16, &mid, 2); memcpy(&l16, &lo, 2);
+        const uint32_t off = (tid >> 3) * 256 + (tid & 7) * 16;
+        *reinterpret_cast<uint4*>(sXA + off) = make_uint4(one | (one << 16), one, 0u, 0u);
+        *reinterpret_cast<uint4*>(sXA + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < p.n) {
+            *reinterpret_cast<uint4*>(sXB + off) = make_uint4((uint32_t)h16 | ((uint32_t)m16 << 16), (uint32_t)l16, 0u, 0u);
+            *reinterpret_cast<uint4*>(sXB + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+    }
     __syncthreads();
     if (tid == 0) {
         mbar_wait(&bar_load, 0, 1);
@@ -134,6 +155,9 @@ bringup_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 umma_ss(tmem, ad, bd, p.idesc, k > 0);
             }
         }
+        if (p.extra_kstep)
+            umma_ss(tmem, make_smem_desc_noswizzle(smem_u32(sXA), p.x_lbo, p.x_sbo),
+                    make_smem_desc_noswizzle(smem_u32(sXB), p.x_lbo, p.x_sbo), p.idesc & ~((1u << 15) | (1u << 16)), 1);
         tc_commit(&bar_mma);
     }
     mbar_wait(&bar_mma, 0, 2);
@@ -207,6 +231,7 @@ struct TestCfg {
     int K, N; bool b_mn_major; bool a_from_tmem; bool bf16; int store_mode;
     uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep; int a_tmem_kstep_cols;
     bool a_mn_major = false;        // A stored [K rows][128 M columns] (M contiguous): the fused backward's dS^T buffer
+    int extra_kstep = 0; uint32_t x_lbo = 0, x_sbo = 0;
 };
 
 static bool run_test(const TestCfg& t) {
@@ -221,6 +246,7 @@ static bool run_test(const TestCfg& t) {
     for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
         float acc = 0.f;
         for (int k = 0; k < K; ++k) acc += (t.a_mn_major ? fA[(size_t)k * M + m] : fA[(size_t)m * K + k]) * (t.b_mn_major ? fB[(size_t)k * N + n] : fB[(size_t)n * K + k]);
+        if (t.extra_kstep) acc += 0.37f * (float)n - 11.5f + 1e-3f * (float)(n * n % 97);
         ref[(size_t)m * N + n] = acc;
     }
     uint16_t *dA, *dB, *dO16; float *dD, *dR;
@@ -242,6 +268,7 @@ static bool run_test(const TestCfg& t) {
     p.idesc = make_idesc(t.bf16, t.a_mn_major, t.b_mn_major, 128, N);
     p.nk = K / 16; p.n = N; p.a_from_tmem = t.a_from_tmem; p.a_tmem_kstep_cols = t.a_tmem_kstep_cols;
     p.bf16 = t.bf16; p.store_mode = t.store_mode;
+    p.extra_kstep = t.extra_kstep; p.x_lbo = t.x_lbo; p.x_sbo = t.x_sbo;
 
     CUtensorMap mA = t.a_mn_major ? make_map_2d(dA, K, M, K, t.bf16) : make_map_2d(dA, M, K, 128, t.bf16);
     CUtensorMap mR = make_map_2d_f32(dR, M, N, 128);
@@ -313,6 +340,9 @@ int main(int argc, char** argv) {
         {"ss_amn_bmn_K128_N64_fp16",       true, 128,  64, true,  false, false, 0, 16384, 1024, 2048, 16384, 1024, 2048, 0, true},
         {"ss_amn_bkmajor_K64_N128_bf16",   true,  64, 128, false, false, true,  0, 8192, 1024, 2048, 0, 1024, 32, 0, true},
         {"ss_amn_swapped_lbo_sbo",         false,128,  64, true,  false, true,  0, 1024, 16384, 2048, 16384, 1024, 2048, 0, true},
+        // statistics through the MMA: one extra K = 16 step from compact no-swizzle tiles (two candidate LBO / SBO readings)
+        {"ss_extra_kstep_noswizzle_lbo128_sbo256", true, 64, 128, false, false, true, 0, 0, 1024, 32, 0, 1024, 32, 0, false, 1, 128, 256},
+        {"ss_extra_kstep_noswizzle_lbo256_sbo128", false, 64, 128, false, false, true, 0, 0, 1024, 32, 0, 1024, 32, 0, false, 1, 256, 128},
         {"tma_reduce_add_f32_sw128_N64",   true, 128,  64, true,  false, true,  2, 0, 1024, 32, 16384, 1024, 2048, 0},
         {"tma_reduce_add_f32_sw128_N128",  true, 128, 128, false, false, true,  2, 0, 1024, 32, 0, 1024, 32, 0},
     };

@@ -207,6 +207,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return kDescSw128 | (uint64_t((sbo_bytes >> 4) & 0x3fff) << 32) |
            (uint64_t((lbo_bytes >> 4) & 0x3fff) << 16) | uint64_t((saddr >> 4) & 0x3fff);
 }
+// Same descriptor without swizzle (bits 61-63 = 0): compact [rows][16 x 16-bit] K-major operands made of 8-row x 16-byte core
+// matrices (128 contiguous bytes each).  Candidate use: one extra K = 16 step that adds per-column statistics to a score tile
+// inside the MMA; encoding pinned by fa_bringup "ss_extra_kstep_noswizzle_*".
+__device__ __forceinline__ uint64_t make_smem_desc_noswizzle(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t(1) << 46) | (uint64_t((sbo_bytes >> 4) & 0x3fff) << 32) |
+           (uint64_t((lbo_bytes >> 4) & 0x3fff) << 16) | uint64_t((saddr >> 4) & 0x3fff);
+}
 // Instruction descriptor, kind::f16 (32-bit):
 //   [4,6) D format: 1 = f32   [7,10) A format: 0 = f16, 1 = bf16   [10,13) B format
 //   [15] A major: 0 = K, 1 = MN   [16] B major   [17,23) N >> 3   [24,29) M >> 4

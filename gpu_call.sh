@@ -1,1 +1,1 @@
-timeout 300 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3 | cut -c1-300
+for i in 19 20 21 22; do timeout 60 ./build/fa_bringup $i 2>&1 | grep -v "^device\|^bringup"; done
