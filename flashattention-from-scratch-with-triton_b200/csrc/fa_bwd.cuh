@@ -136,20 +136,34 @@ __device__ __forceinline__ void stage_grad_half(uint32_t t_acc, uint8_t* stage, 
 #define FA_BWD_PERSISTENT 1     // 0: grid = one CTA per item through the same code (A/B switch)
 #endif
 
+// Statistics through the MMA: instead of 32 broadcast LDS.128 per thread and tile (30 % of the shared-memory
+// pipe in the D=128 dK/dV kernel), -LSE/scale and -delta ride the two score MMAs as ONE extra K = 16 step:
+//   S'^T = K Q^T + ones (x) a^T,  a_q = 3-way bf16 split of -LSE_q / scale;   dP'^T = V dO^T + ones (x) b^T,  b_q = split of -delta_q
+// from compact no-swizzle tiles (encoding and precision pinned by fa_bringup ss_extra_kstep_noswizzle_*: max error 3.8e-6).
+// The math warps then compute P = exp2(c S') and dS = P o dP' with no shared-memory reads.  Off until measured.
+#ifndef FA_STATS_MMA
+#define FA_STATS_MMA 0
+#endif
+constexpr bool kStatsMma = FA_STATS_MMA != 0;
+
 template <int D> struct DkvCfg {
     static constexpr int kChunks = D / 64;
     static constexpr int kTileBytes = 128 * D * 2;
     static constexpr int kStages = (D == 128) ? 2 : 4;
-    static constexpr int kStatStages = 8;
+    // plain: 8 slots x 1 KB (128 fp32 + 128 fp32); through the MMA: 3 slots x 2 compact [128 x 16] bf16 tiles + the ones tile
+    static constexpr int kStatStages = kStatsMma ? 3 : 8;
+    static constexpr int kStatSlotBytes = kStatsMma ? 8192 : 1024;
+    static constexpr int kStatBytes = kStatStages * kStatSlotBytes + (kStatsMma ? 4096 : 0);
     static constexpr bool kSepStage = (D == 64);          // own dK/dV staging: next K/V can land under the epilogue
     static constexpr int kOffRes = 0;
     static constexpr int kOffStage = 2 * kTileBytes;
     static constexpr int kStageBytes = 2 * kTileBytes;
     static constexpr int kOffStat = kOffStage + kStages * kStageBytes;
-    static constexpr int kOffOut = kOffStat + kStatStages * 1024;
+    static constexpr int kOffOut = kOffStat + kStatBytes;
     static constexpr int kOffBar = kOffOut + (kSepStage ? 2 * kTileBytes : 0);
     static constexpr int kNumBars = 16 + 3 * kStages + 2 * kStatStages;
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 32 + 1024;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // kDropout: instantiation that regenerates the forward's keep mask (fa_ptx.cuh): dV uses the dropped-out, rescaled P^T,
@@ -193,7 +207,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         mbar_init(kv_free, C::kSepStage ? 1 : 2);         // MMA thread (+ the store's read-done when staging aliases K/V)
         for (int i = 0; i < 2; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 10); }
         for (int i = 0; i < C::kStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&do_full[i], 1); mbar_init(&stage_empty[i], 1); }
-        for (int i = 0; i < C::kStatStages; ++i) { mbar_init(&stat_full[i], 1); mbar_init(&stat_empty[i], 8); }
+        for (int i = 0; i < C::kStatStages; ++i) { mbar_init(&stat_full[i], 1); mbar_init(&stat_empty[i], kStatsMma ? 1 : 8); }
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -241,6 +255,19 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const int lane = lane_id();
         const uint32_t stat_addr = smem_u32(sStat);
         uint32_t gs = 0;
+        if constexpr (kStatsMma) {
+            // once: zero every compact tile (their second 16-byte K chunk is never written again) and build the ones tile
+            // [128 x 16] = {1, 1, 1, 0 ...} behind the slots; the first stat_full arrive publishes all of it
+            for (uint32_t o = lane * 16; o < (uint32_t)C::kStatBytes; o += 32 * 16) sts128(stat_addr + o, 0u, 0u, 0u, 0u);
+            __syncwarp();
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t q = lane * 4 + u;
+                sts128(stat_addr + C::kStatStages * C::kStatSlotBytes + (q >> 3) * 256 + (q & 7) * 16, 0x3f803f80u, 0x3f80u, 0u, 0u);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+        }
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
@@ -278,8 +305,29 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             auto publish = [&](const float4& nl, const float4& dl) {
                 const uint32_t ss = gs % C::kStatStages;
                 mbar_wait(&stat_empty[ss], ((gs / C::kStatStages) & 1) ^ 1, 400);
-                sts128(stat_addr + ss * 1024 + lane * 16, __float_as_uint(nl.x), __float_as_uint(nl.y), __float_as_uint(nl.z), __float_as_uint(nl.w));
-                sts128(stat_addr + ss * 1024 + 512 + lane * 16, __float_as_uint(dl.x), __float_as_uint(dl.y), __float_as_uint(dl.z), __float_as_uint(dl.w));
+                if constexpr (kStatsMma) {
+                    // row q = 4 lane + u of the two compact tiles: [hi, mid, lo, 0 ...] of nl / c = -LSE / scale and of -delta
+                    const float inv_c = 1.0f / p.scale_log2;
+                    const float nv[4] = {nl.x, nl.y, nl.z, nl.w}, dv[4] = {dl.x, dl.y, dl.z, dl.w};
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t q = lane * 4 + u, off = (q >> 3) * 256 + (q & 7) * 16;
+                        #pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+                            const float x = w ? dv[u] : ((nv[u] == -INFINITY) ? -INFINITY : nv[u] * inv_c);
+                            const __nv_bfloat16 hi = __float2bfloat16(x);
+                            const float r1 = (x == -INFINITY) ? 0.f : x - __bfloat162float(hi);
+                            const __nv_bfloat16 mid = __float2bfloat16(r1);
+                            const __nv_bfloat16 lo = __float2bfloat16(r1 - __bfloat162float(mid));
+                            const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+                            sts128(stat_addr + ss * C::kStatSlotBytes + w * 4096 + off, w0, (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                } else {
+                    sts128(stat_addr + ss * 1024 + lane * 16, __float_as_uint(nl.x), __float_as_uint(nl.y), __float_as_uint(nl.z), __float_as_uint(nl.w));
+                    sts128(stat_addr + ss * 1024 + 512 + lane * 16, __float_as_uint(dl.x), __float_as_uint(dl.y), __float_as_uint(dl.z), __float_as_uint(dl.w));
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&stat_full[ss]);
                 ++gs;
@@ -357,19 +405,40 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             auto qfull = [&](uint32_t g) { mbar_wait(&q_full[g % C::kStages], (g / C::kStages) & 1, 421); };
             auto dofull = [&](uint32_t g) { mbar_wait(&do_full[g % C::kStages], (g / C::kStages) & 1, 423); };
             auto stage_addr = [&](uint32_t g) { return aSt + (g % C::kStages) * C::kStageBytes; };
+            // statistics through the MMA: one more K = 16 step, ones (x) split(-LSE/scale) on S^T(G), ones (x) split(-delta) on dP^T(G);
+            // the slot of iteration G is awaited at S^T(G) (always issued first) and released behind dP^T(G)
+            const uint32_t aStat = smem_u32(sStat), aOnes = aStat + C::kStatStages * C::kStatSlotBytes;
+            auto stat_scores = [&](uint32_t d_tmem, uint32_t G) {
+                if constexpr (kStatsMma) {
+                    mbar_wait(&stat_full[G % C::kStatStages], (G / C::kStatStages) & 1, 427); tc_fence_after();
+                    umma_ss_e(d_tmem, make_smem_desc_noswizzle(aOnes, 128, 256),
+                              make_smem_desc_noswizzle(aStat + (G % C::kStatStages) * C::kStatSlotBytes, 128, 256),
+                              make_idesc(true, false, false, 128, 128), 1);
+                }
+            };
+            auto stat_dp = [&](uint32_t G) {
+                if constexpr (kStatsMma) {
+                    umma_ss_e(tmem + kColDPT, make_smem_desc_noswizzle(aOnes, 128, 256),
+                              make_smem_desc_noswizzle(aStat + (G % C::kStatStages) * C::kStatSlotBytes + 4096, 128, 256),
+                              make_idesc(true, false, false, 128, 128), 1);
+                    tc_commit_e(&stat_empty[G % C::kStatStages]);
+                }
+            };
             if (n_it > 0) {
                 mbar_wait(k_full, nacc & 1, 420);
                 qfull(git); tc_fence_after();
                 issue_scores<D, kBf16>(tmem + kColST + (kDoubleS ? (gi & 1) * 128 : 0), aK, stage_addr(git));
+                stat_scores(tmem + kColST + (kDoubleS ? (gi & 1) * 128 : 0), gi);
                 tc_commit_e((kDoubleS && (gi & 1)) ? s_full1 : s_full);
                 if (kDoubleS && n_it > 1) {
                     qfull(git + 1); tc_fence_after();
                     issue_scores<D, kBf16>(tmem + kColST + ((gi + 1) & 1) * 128, aK, stage_addr(git + 1));
+                    stat_scores(tmem + kColST + ((gi + 1) & 1) * 128, gi + 1);
                     tc_commit_e(((gi + 1) & 1) ? s_full1 : s_full);
                 }
                 mbar_wait(v_full, nacc & 1, 422);
                 dofull(git); tc_fence_after();
-                issue_scores<D, kBf16>(tmem + kColDPT, aV, stage_addr(git) + C::kTileBytes); tc_commit_e(dp_full);
+                issue_scores<D, kBf16>(tmem + kColDPT, aV, stage_addr(git) + C::kTileBytes); stat_dp(gi); tc_commit_e(dp_full);
             }
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it, gt = git + it;
@@ -384,18 +453,21 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     if (it + 2 < n_it) {                                                   // S^T(i+2) into the buffer dV(i) just read
                         qfull(gt + 2); tc_fence_after();
                         issue_scores<D, kBf16>(tmem + kColST + sbuf, aK, stage_addr(gt + 2));
+                        stat_scores(tmem + kColST + sbuf, g + 2);
                         tc_commit_e((g & 1) ? s_full1 : s_full);
                     }
                 } else if (more) {
                     qfull(gt + 1); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColST, aK, stage_addr(gt + 1)); tc_commit_e(s_full);     // S^T(i+1)
+                    issue_scores<D, kBf16>(tmem + kColST, aK, stage_addr(gt + 1)); stat_scores(tmem + kColST, g + 1);
+                    tc_commit_e(s_full);                                                                       // S^T(i+1)
                 }
                 mbar_wait(ds_full, g & 1, 426); tc_fence_after();
                 issue_grad<D, kBf16>(tmem + kColDK, tmem + kColDPT, aQ, it > 0);           // dK += dS^T Q_i
                 tc_commit_e(&stage_empty[gt % C::kStages]);
                 if (more) {
                     dofull(gt + 1); tc_fence_after();
-                    issue_scores<D, kBf16>(tmem + kColDPT, aV, stage_addr(gt + 1) + C::kTileBytes); tc_commit_e(dp_full);   // dP^T(i+1)
+                    issue_scores<D, kBf16>(tmem + kColDPT, aV, stage_addr(gt + 1) + C::kTileBytes); stat_dp(g + 1);
+                    tc_commit_e(dp_full);                                                                      // dP^T(i+1)
                 }
             }
             if (n_it == 0) mbar_wait(acc_empty, (ix & 1) ^ 1, 429);
@@ -434,7 +506,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 const int q0 = qtile * 128 + h * 64;                 // global query index of my column 0
                 const uint32_t bhq_it = bhq;
                 if (++qtile == i_end) { qtile = i_start; ++bhq; }
-                mbar_wait(&stat_full[ss], (g / C::kStatStages) & 1, 430);
+                if constexpr (!kStatsMma) mbar_wait(&stat_full[ss], (g / C::kStatStages) & 1, 430);
                 const uint32_t tSTi = tST + (kDoubleS ? (g & 1) * 128 : 0);
                 if (kDoubleS) mbar_wait((g & 1) ? s_full1 : s_full, (g >> 1) & 1, 431);
                 else mbar_wait(s_full, g & 1, 431);
@@ -448,9 +520,15 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     const uint64_t c2v = pack_f2(c2, c2);
                     #pragma unroll
                     for (int c = 0; c < 64; c += 4) {
-                        const float4 nl = lds128(stat + c * 4);
-                        const uint64_t xa = ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, pack_f2(nl.x, nl.y));
-                        const uint64_t xb = ffma2(pack_u2(s[c >> 5][(c & 31) + 2], s[c >> 5][(c & 31) + 3]), c2v, pack_f2(nl.z, nl.w));
+                        uint64_t xa, xb;
+                        if constexpr (kStatsMma) {               // the MMA already added -LSE / scale
+                            xa = fmul2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v);
+                            xb = fmul2(pack_u2(s[c >> 5][(c & 31) + 2], s[c >> 5][(c & 31) + 3]), c2v);
+                        } else {
+                            const float4 nl = lds128(stat + c * 4);
+                            xa = ffma2(pack_u2(s[c >> 5][c & 31], s[c >> 5][(c & 31) + 1]), c2v, pack_f2(nl.x, nl.y));
+                            xb = ffma2(pack_u2(s[c >> 5][(c & 31) + 2], s[c >> 5][(c & 31) + 3]), c2v, pack_f2(nl.z, nl.w));
+                        }
                         if ((c & 15) < BwdPoly<D>::kDkv) {
                             ex2_poly2(xa, pv[c], pv[c + 1]); ex2_poly2(xb, pv[c + 2], pv[c + 3]);
                         } else {
@@ -502,7 +580,8 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                         #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
                             const int c = q * 32 + 2 * i;
-                            const float4 dl = lds128(stat + 512 + c * 4);
+                            float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);             // through the MMA: dP' already holds dP - delta
+                            if constexpr (!kStatsMma) dl = lds128(stat + 512 + c * 4);
                             float d0, d1, d2, d3;        // dS = P o (dP - delta), packed: FADD2 + FMUL2
                             uint64_t dpa = pack_u2(dp[q][2 * i], dp[q][2 * i + 1]), dpb = pack_u2(dp[q][2 * i + 2], dp[q][2 * i + 3]);
                             if constexpr (kDropout) {
@@ -510,8 +589,9 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                                 dpa = pack_f2(((keep >> c) & 1) ? e0 * p.drop.scale : 0.f, ((keep >> (c + 1)) & 1) ? e1 * p.drop.scale : 0.f);
                                 dpb = pack_f2(((keep >> (c + 2)) & 1) ? e2 * p.drop.scale : 0.f, ((keep >> (c + 3)) & 1) ? e3 * p.drop.scale : 0.f);
                             }
-                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), fadd2(dpa, pack_f2(dl.x, dl.y))), d0, d1);
-                            unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]), fadd2(dpb, pack_f2(dl.z, dl.w))), d2, d3);
+                            if constexpr (!kStatsMma) { dpa = fadd2(dpa, pack_f2(dl.x, dl.y)); dpb = fadd2(dpb, pack_f2(dl.z, dl.w)); }
+                            unpack_f2(fmul2(pack_f2(pv[c], pv[c + 1]), dpa), d0, d1);
+                            unpack_f2(fmul2(pack_f2(pv[c + 2], pv[c + 3]), dpb), d2, d3);
                             pk[i] = pack2<kBf16>(d0, d1); pk[i + 1] = pack2<kBf16>(d2, d3);
                         }
                         tmem_st16(tDPT + q * 16, pk);
@@ -519,8 +599,10 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 }
                 tc_wait_st(); tc_fence_before();
                 mbar_arrive(ds_full);
-                __syncwarp();
-                if (lane_id() == 0) mbar_arrive(&stat_empty[ss]);    // this warp is done with the slot's statistics
+                if constexpr (!kStatsMma) {
+                    __syncwarp();
+                    if (lane_id() == 0) mbar_arrive(&stat_empty[ss]);    // this warp is done with the slot's statistics
+                }
             }
             gi += n_it;
             // ---- epilogue: dV, dK*scale -> 16-bit -> smem staging -> TMA store
@@ -873,6 +955,7 @@ template <int D, bool kBf16>
 int launch_bwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
                  const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
                  int parts, cudaStream_t st) {
+    if (kStatsMma && p.drop.thresh) return (int)cudaErrorNotSupported;   // experimental build: dP - delta is formed inside the MMA, dropout must scale dP alone
     return p.drop.thresh ? launch_bwd_td<D, kBf16, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, parts, st)
                          : launch_bwd_td<D, kBf16, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, parts, st);
 }
