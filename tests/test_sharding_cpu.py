@@ -120,3 +120,69 @@ def test_zigzag_split_roundtrip_and_balance():
             a, b = sh.zigzag_chunks(r, W)
             work.append((a + 1) + (b + 1))
         assert len(set(work)) == 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Range masks: the kernels take an item's tile range from the FIRST and LAST row of its tile (csrc/fa_fwd.cuh::fwd_item_iters,
+# the dK/dV decode in csrc/fa_bwd.cuh).  That is only right because the ranges are monotone; this restates the two formulas and
+# checks by brute force that no visible (query, key) pair ever falls outside the tiles a kernel would visit.
+# ---------------------------------------------------------------------------------------------------------------------
+def _fwd_item_iters(row_lo, row_hi, q0, t, Sq, Sk, causal):
+    jb = int(row_lo[min(q0, Sq - 1)]) >> 7
+    r0 = q0 + t * 128
+    if r0 >= Sq:
+        return jb, 0
+    last = min(r0 + 127, Sq - 1)
+    hi = min(int(row_hi[last]), Sk)
+    if causal:
+        hi = min(hi, last + 1)
+    return jb, max(((hi - 1) >> 7) - jb + 1, 0)
+
+
+def _dkv_item_range(col_lo, col_hi, jt, Sq, Sk, causal):
+    n_qtiles = (Sq + 127) // 128
+    i_start = jt if causal else 0
+    i_start = max(i_start, int(col_lo[min(jt * 128, Sk - 1)]) >> 7)
+    i_end = min(n_qtiles, ((min(int(col_hi[min(jt * 128 + 127, Sk - 1)]), Sq) - 1) >> 7) + 1)
+    return i_start, i_end
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_range_mask_tile_ranges_cover_every_visible_pair(causal):
+    import flashattn_b200 as fa
+    rng = torch.Generator().manual_seed(11)
+    cases = []
+    for _ in range(6):                                   # random packings: boundaries inside tiles, on tile edges, 1-token sequences
+        lens = torch.randint(1, 400, (int(torch.randint(2, 9, (1,), generator=rng)),), generator=rng).tolist()
+        cu = [0]
+        for n in lens:
+            cu.append(cu[-1] + n)
+        cases.append((fa.Ranges.from_cu_seqlens(cu, cu[-1]), cu[-1], cu[-1]))
+    cases.append((fa.Ranges.from_key_padding([77, 300], 300, 300), 300, 300))
+    if causal:
+        cases.append((fa.Ranges.sliding_window(1, 700, 130), 700, 700))
+    for r, Sq, Sk in cases:
+        for b in range(r.row_lo.shape[0]):
+            lo, hi, clo, chi = r.row_lo[b], r.row_hi[b], r.col_lo[b], r.col_hi[b]
+            i = torch.arange(Sq)[:, None]; j = torch.arange(Sk)[None, :]
+            vis = (j >= lo[:, None]) & (j < hi[:, None])
+            if causal:
+                vis &= (i >= j)
+            assert torch.equal(vis, (i >= clo[None, :]) & (i < chi[None, :]) & ((i >= j) if causal else True))
+            # forward / dQ orientation: 256-row items, two 128-row tiles sharing one K/V stream that starts at tile jb
+            for q0 in range(0, Sq, 256):
+                for t in (0, 1):
+                    jb, nt = _fwd_item_iters(lo, hi, q0, t, Sq, Sk, causal)
+                    rows = vis[q0 + t * 128:q0 + t * 128 + 128]
+                    if rows.numel() == 0:
+                        assert nt == 0
+                        continue
+                    keys = torch.nonzero(rows.any(0)).flatten()
+                    if keys.numel():
+                        assert jb * 128 <= int(keys.min()) and int(keys.max()) < (jb + nt) * 128, (q0, t, jb, nt)
+            # dK/dV orientation: one 128-row kv tile, q tiles [i_start, i_end)
+            for jt in range((Sk + 127) // 128):
+                i_start, i_end = _dkv_item_range(clo, chi, jt, Sq, Sk, causal)
+                qs = torch.nonzero(vis[:, jt * 128:jt * 128 + 128].any(1)).flatten()
+                if qs.numel():
+                    assert i_start * 128 <= int(qs.min()) and int(qs.max()) < i_end * 128, (jt, i_start, i_end)
