@@ -86,6 +86,34 @@ def build_bringup(force: bool = False) -> str:
     return BRINGUP
 
 
+TORCH_EXT = os.path.join(PKG, "_fa_torch.so")
+
+
+def build_torch_ext(force: bool = False, verbose: bool = False) -> str:
+    """_fa_torch.so: the C++ autograd host path (csrc/fa_torch.cpp) — host code only, compiled with g++ against the torch
+    headers and linked to libfa_sm100.so next to it (rpath $ORIGIN).  In-tree, so it travels to the GPU box."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    build_lib()
+    src = os.path.join(CSRC, "fa_torch.cpp")
+    if not force and not _stale(TORCH_EXT, [src, os.path.join(ROOT, "include", "fa_sm100.h")]):
+        return TORCH_EXT
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DTORCH_EXTENSION_NAME=_fa_torch", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           *[f"-I{d}" for d in ce.include_paths()], f"-I{sysconfig.get_paths()['include']}", f"-I{cuda_inc}",
+           src, "-o", TORCH_EXT, f"-L{PKG}", "-l:libfa_sm100.so", f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10",
+           "-lc10_cuda", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}", "-Wno-deprecated-declarations"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed building _fa_torch.so")
+    return TORCH_EXT
+
+
 MICROBENCH = os.path.join(ROOT, "build", "fa_microbench")
 
 
@@ -114,6 +142,7 @@ if __name__ == "__main__":
         name, _, defs = v.partition(":")
         print(build_variant(name, [d for d in defs.split(",") if d]))
     print(build_lib(a.force, a.verbose))
+    print(build_torch_ext(a.force, a.verbose))
     if a.bringup:
         print(build_bringup(a.force))
         print(build_microbench(a.force))

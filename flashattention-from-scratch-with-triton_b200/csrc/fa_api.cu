@@ -88,17 +88,18 @@ bool strides_ok(RowStrides& st, int B, int H, int S, int D) {
 }
 
 // `ready` publishes the other fields (release / acquire): concurrent first calls on one device are safe
-struct DeviceInfo { int sms = 0; int cc_major = 0; unsigned int* sched_ring = nullptr; std::atomic<int> ready{0}; };
+struct DeviceInfo { int ordinal = 0; int sms = 0; int cc_major = 0; unsigned int* sched_ring = nullptr; std::atomic<int> ready{0}; };
 constexpr int kMaxDevices = 64;
-constexpr int kSchedRing = 1024;
-__device__ unsigned int g_sched_ring[kSchedRing];
+// Work-counter ring of the persistent kernels (one instance per device: a __device__ symbol).  A launch takes one UNIT = 4 words =
+// two self-resetting {work counter, retired-CTA counter} pairs (sched_retire), handed out round-robin with a single power-of-two
+// modulus, so two allocations never overlap partially.  A unit is reused after kSchedUnits later launches of the process: the
+// library supports up to kSchedUnits (4096) launches pending at once across all streams and captured graphs of a device.
+constexpr unsigned int kSchedUnits = 4096;
+__device__ unsigned int g_sched_ring[kSchedUnits * 4];
 DeviceInfo g_dev[kMaxDevices];
 std::mutex g_dev_mu;
 std::atomic<unsigned int> g_sched_next{0};
-// `pairs` consecutive {work counter, retired-CTA counter} pairs from the ring (zero at load time, self-resetting afterwards)
-unsigned int sched_slot(unsigned int pairs) {
-    return (g_sched_next.fetch_add(pairs) % (kSchedRing / 2 - pairs)) * 2;
-}
+unsigned int sched_slot() { return (g_sched_next.fetch_add(1u, std::memory_order_relaxed) & (kSchedUnits - 1u)) * 4u; }
 
 int device_info(DeviceInfo** out) {
     int dev = 0;
@@ -115,7 +116,7 @@ int device_info(DeviceInfo** out) {
             void* ring = nullptr;
             e = cudaGetSymbolAddress(&ring, g_sched_ring);
             if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(sched ring) — was the library built for sm_100a?");
-            d.cc_major = major; d.sched_ring = (unsigned int*)ring; d.sms = sms;
+            d.ordinal = dev; d.cc_major = major; d.sched_ring = (unsigned int*)ring; d.sms = sms;
             d.ready.store(1, std::memory_order_release);
         }
     }
@@ -154,28 +155,23 @@ int make_dropout(const fa_sm100_options* opt, DropoutParams* d) {
     return 0;
 }
 
-template <typename K> cudaError_t set_smem(K kernel, int bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
-
 template <int D, bool kBf16, bool kRanges, bool kDropout>
 int launch_fwd_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
-                 const FwdParams& p, int grid, cudaStream_t st) {
-    static std::once_flag once; static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = set_smem(fa_fwd_kernel<D, kBf16, kRanges, kDropout>, FwdCfg<D>::kSmemBytes); });
-    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(fwd smem)");
-    cudaError_t e = launch_pdl(fa_fwd_kernel<D, kBf16, kRanges, kDropout>, grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st, mq, mk, mv, mo, p);
+                 const FwdParams& p, int grid, int dev, cudaStream_t st) {
+    cudaError_t e = ensure_smem<fa_fwd_kernel<D, kBf16, kRanges, kDropout>>(FwdCfg<D>::kSmemBytes, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fwd smem)");
+    e = launch_pdl(fa_fwd_kernel<D, kBf16, kRanges, kDropout>, grid, kFwdThreads, FwdCfg<D>::kSmemBytes, st, mq, mk, mv, mo, p);
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "fa_fwd_kernel launch");
 }
 template <int D, bool kBf16>
 int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
-               const FwdParams& p, int grid, cudaStream_t st) {
-    if (p.drop.thresh) return p.row_lo ? launch_fwd_t<D, kBf16, true, true>(mq, mk, mv, mo, p, grid, st)
-                                       : launch_fwd_t<D, kBf16, false, true>(mq, mk, mv, mo, p, grid, st);
-    return p.row_lo ? launch_fwd_t<D, kBf16, true, false>(mq, mk, mv, mo, p, grid, st)
-                    : launch_fwd_t<D, kBf16, false, false>(mq, mk, mv, mo, p, grid, st);
+               const FwdParams& p, int grid, int dev, cudaStream_t st) {
+    if (p.drop.thresh) return p.row_lo ? launch_fwd_t<D, kBf16, true, true>(mq, mk, mv, mo, p, grid, dev, st)
+                                       : launch_fwd_t<D, kBf16, false, true>(mq, mk, mv, mo, p, grid, dev, st);
+    return p.row_lo ? launch_fwd_t<D, kBf16, true, false>(mq, mk, mv, mo, p, grid, dev, st)
+                    : launch_fwd_t<D, kBf16, false, false>(mq, mk, mv, mo, p, grid, dev, st);
 }
 
 }  // namespace
@@ -249,11 +245,11 @@ int fa_sm100_fwd_opt(const void* q, const void* k, const void* v, void* o, float
     p.scale_log2 = p.scale * 1.44269504088896340736f;
     p.lse = lse;
     p.row_lo = row_lo; p.row_hi = row_hi; p.drop = drop;
-    p.sched = dev->sched_ring + sched_slot(1);          // self-resetting counter pair (sched_retire): no memset on the stream
+    p.sched = dev->sched_ring + sched_slot();           // self-resetting counter pair (sched_retire): no memset on the stream
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = p.n_items < dev->sms ? p.n_items : dev->sms;
-    if (D == 64) return dtype ? launch_fwd<64, true>(mq, mk, mv, mo, p, grid, st) : launch_fwd<64, false>(mq, mk, mv, mo, p, grid, st);
-    return dtype ? launch_fwd<128, true>(mq, mk, mv, mo, p, grid, st) : launch_fwd<128, false>(mq, mk, mv, mo, p, grid, st);
+    if (D == 64) return dtype ? launch_fwd<64, true>(mq, mk, mv, mo, p, grid, dev->ordinal, st) : launch_fwd<64, false>(mq, mk, mv, mo, p, grid, dev->ordinal, st);
+    return dtype ? launch_fwd<128, true>(mq, mk, mv, mo, p, grid, dev->ordinal, st) : launch_fwd<128, false>(mq, mk, mv, mo, p, grid, dev->ordinal, st);
 }
 
 int fa_sm100_delta(const void* o, const void* dout, float* delta, int B, int H, int Sq, int D, int dtype, void* stream) {
@@ -362,9 +358,10 @@ int fa_sm100_bwd_opt(const void* q, const void* k, const void* v, const void* o,
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
     p.hc_dkv = heads_per_chunk(BH / p.G, 4.0 * ((double)p.G * Sq + Sk) * D);
     {   // two self-resetting counter pairs from the ring
-        const unsigned int slot = sched_slot(2);
+        const unsigned int slot = sched_slot();
         p.sched_dkv = dev->sched_ring + slot; p.sched_dq = dev->sched_ring + slot + 2;
     }
+    p.dev = dev->ordinal;
     rc = launch_bwd(mq, mk, mv, mdo, mdq, mdk, mdv, p, D, dtype, parts, st);
     g_launches += ((parts & FA_BWD_DQ) ? 1 : 0) + ((parts & FA_BWD_DKV) ? 1 : 0);
     return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_bwd kernels launch");
@@ -433,7 +430,8 @@ int fa_sm100_bwd_fused_opt(const void* q, const void* k, const void* v, const vo
     p.sms = dev->sms;
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
     p.hc_dkv = heads_per_chunk(BH / p.G, 4.0 * ((double)p.G * Sq + Sk) * D);
-    p.sched_dkv = dev->sched_ring + sched_slot(1); p.sched_dq = nullptr;
+    p.sched_dkv = dev->sched_ring + sched_slot(); p.sched_dq = nullptr;
+    p.dev = dev->ordinal;
     rc = dtype ? launch_bwd_fused_t<true>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts)
                : launch_bwd_fused_t<false>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts);
     g_launches += ((parts & FA_BWD_FUSED) ? 1 : 0) + ((parts & FA_BWD_CONVERT) ? 1 : 0);

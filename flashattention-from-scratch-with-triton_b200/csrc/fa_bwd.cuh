@@ -37,6 +37,7 @@ struct BwdParams {
     unsigned int* sched_dkv;   // work counters (zeroed before launch) for the persistent kernels
     unsigned int* sched_dq;
     int sms;
+    int dev;                   // device ordinal of the launch (host side only: per-device kernel attributes)
     int hc_dkv, hc_dq;         // heads per scheduling chunk (item_to_head_tile) for the K/V-tile and the Q-tile kernels
     // Optional range masks (FwdParams): row_lo/row_hi [B, Sq] = keys visible to a query row (used by the dQ kernel);
     // col_lo/col_hi [B, Sk] = queries that see a key row (the same mask seen from the K/V side, used by the dK/dV kernel).
@@ -633,6 +634,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem, 512);
+    hang_trap_if_set();
 }
 
 // =================================================================================================
@@ -734,9 +736,11 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             if (item >= n_items) break;
             int bh, iq, jb, n_it; decode(item, bh, iq, jb, n_it);
             mbar_wait(qdo_free, (ix & 1) ^ 1, 542);          // Q/dO smem of the previous item released
-            mbar_arrive_expect_tx_e(q_full, C::kTileBytes);
-            #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh % p.H, bh / p.H);
+            if (n_it > 0) {                                  // n_it == 0: no row of the tile sees a key (range masks) -> dQ = 0, no loads
+                mbar_arrive_expect_tx_e(q_full, C::kTileBytes);
+                #pragma unroll
+                for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sQ + c * 16384, &mapQ, q_full, c * 64, iq * 128, bh % p.H, bh / p.H);
+            }
             for (int it = 0; it < n_it; ++it, ++g) {
                 const uint32_t ks = g % C::kKStages, vs = g % C::kVStages;
                 uint8_t* sKj = sKr + ks * C::kTileBytes;
@@ -763,20 +767,25 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         // ---------------------------------- MMA issuer (whole warp, converged) ----------------------------------
         reg_dealloc<BwdRegs<D>::kOther>();
         const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKr = smem_u32(sKr), aVr = smem_u32(sVr);
-        uint32_t gi = 0;
+        uint32_t gi = 0, nld = 0;                      // nld: items that loaded Q / dO (phase of q_full / do_full)
         for (uint32_t ix = 0;; ++ix) {
             const int item = next_item(ix);
             if (item >= n_items) break;
             int bh, iq, jb, n_it; decode(item, bh, iq, jb, n_it);
             auto kfull = [&](uint32_t g) { mbar_wait(&k_full[g % C::kKStages], (g / C::kKStages) & 1, 521); };
             auto vfull = [&](uint32_t g) { mbar_wait(&v_full[g % C::kVStages], (g / C::kVStages) & 1, 523); };
-            mbar_wait(q_full, ix & 1, 520);
-            kfull(gi); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColS, aQ, aKr + (gi % C::kKStages) * C::kTileBytes); tc_commit_e(s_full);
-            mbar_wait(do_full, ix & 1, 522);
-            vfull(gi); tc_fence_after();
-            issue_scores<D, kBf16>(tmem + kColDP, adO, aVr + (gi % C::kVStages) * C::kTileBytes); tc_commit_e(dp_full);
-            tc_commit_e(&v_empty[gi % C::kVStages]);
+            if (n_it > 0) {
+                mbar_wait(q_full, nld & 1, 520);
+                kfull(gi); tc_fence_after();
+                issue_scores<D, kBf16>(tmem + kColS, aQ, aKr + (gi % C::kKStages) * C::kTileBytes); tc_commit_e(s_full);
+                mbar_wait(do_full, nld & 1, 522);
+                vfull(gi); tc_fence_after();
+                issue_scores<D, kBf16>(tmem + kColDP, adO, aVr + (gi % C::kVStages) * C::kTileBytes); tc_commit_e(dp_full);
+                tc_commit_e(&v_empty[gi % C::kVStages]);
+                ++nld;
+            } else {
+                mbar_wait(acc_empty, (ix & 1) ^ 1, 529);   // keep the accumulator hand-shake in step: the math warps store zeros
+            }
             for (int it = 0; it < n_it; ++it) {
                 const uint32_t g = gi + it;
                 if (it + 1 < n_it) {
@@ -903,7 +912,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 if (tid == 0 && store_pending) tma_store_wait_read0();
                 named_bar_sync(1, 256);
             }
-            stage_grad_half<D, kBf16>(tmem + lane_field + kColDQ, sOut, r, h, p.scale, false);
+            stage_grad_half<D, kBf16>(tmem + lane_field + kColDQ, sOut, r, h, p.scale, n_it == 0);
             tc_fence_before();
             mbar_arrive(acc_empty);                          // dQ drained from TMEM
             fence_proxy_async_smem();
@@ -921,19 +930,18 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem, 512);
+    hang_trap_if_set();
 }
 
 template <int D, bool kBf16, bool kDropout>
 int launch_bwd_td(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
                   const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const BwdParams& p,
                   int parts, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(fa_bwd_dkv_kernel<D, kBf16, kDropout>, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg<D>::kSmemBytes);
+    {
+        cudaError_t e = ensure_smem<fa_bwd_dkv_kernel<D, kBf16, kDropout>>(DkvCfg<D>::kSmemBytes, p.dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(fa_bwd_dq_kernel<D, kBf16, kDropout>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D>::kSmemBytes);
+        e = ensure_smem<fa_bwd_dq_kernel<D, kBf16, kDropout>>(DqCfg<D>::kSmemBytes, p.dev);
         if (e != cudaSuccess) return (int)e;
-        attr_done = true;
     }
     // same order as the reference launcher (code/My_FlashAttention_optimized.py:111-126): dQ, then dK/dV
     if (parts & 2) {

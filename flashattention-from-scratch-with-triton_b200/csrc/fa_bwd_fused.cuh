@@ -570,6 +570,7 @@ fa_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem, 512);
+    hang_trap_if_set();
 }
 
 // dq[b,h,s,:] = scale * accumulator[b,h,s,:]  (fp32 contiguous [B*H, Sq, D] -> 16-bit, any strides); four rows per thread,
@@ -609,11 +610,9 @@ int launch_bwd_fused_te(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
                         const CUtensorMap& mdk, const CUtensorMap& mdv, const CUtensorMap& macc, const BwdParams& p,
                         const float* acc, void* dq, RowStrides s_dq, cudaStream_t st, int parts) {
     constexpr int D = 64;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(fa_bwd_fused_kernel<D, kBf16, kExt>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<D>::kSmemBytes);
+    {
+        cudaError_t e = ensure_smem<fa_bwd_fused_kernel<D, kBf16, kExt>>(FusedCfg<D>::kSmemBytes, p.dev);
         if (e != cudaSuccess) return (int)e;
-        attr_done = true;
     }
     const int items = (p.BH / p.G) * p.n_ktiles;
     const int grid = items < p.sms ? items : p.sms;

@@ -201,11 +201,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         tma_load_4d_e(sKV + st * C::kTileBytes + c * 16384, m, &kv_full[st], c * 64, (jb + j) * 128, (bh % p.H) / p.G, bh / p.H);
                     ++kv_cnt;
                 };
-                if (n0 > 0) load_q(0, q_cnt0);
-                load_kv(&mapK, 0);
-                if (n1 > 0) load_q(1, q_cnt1);
-                load_kv(&mapV, 0);
-                for (int j = 1; j < n; ++j) { load_kv(&mapK, j); load_kv(&mapV, j); }
+                if (n > 0) {                              // n == 0: no row of the item sees a key (range masks) -> nothing to load
+                    if (n0 > 0) load_q(0, q_cnt0);
+                    load_kv(&mapK, 0);
+                    if (n1 > 0) load_q(1, q_cnt1);
+                    load_kv(&mapV, 0);
+                    for (int j = 1; j < n; ++j) { load_kv(&mapK, j); load_kv(&mapV, j); }
+                }
                 if (lane_id() == 0) item = (int)atomicAdd(p.sched, 1u) + (int)gridDim.x;
                 item = __shfl_sync(0xffffffffu, item, 0);
             }
@@ -285,7 +287,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         mbar_arrive_e(&kv_empty[st]);
                     }
                 };
-                do_s(0);
+                if (n > 0) do_s(0);
                 for (int j = 0; j < n; ++j) {
                     if (C::kSepP) {                        // S_t(j+1) does not depend on P_t(j) V(j): issue it first
                         if (j + 1 < n) do_s(j + 1);
@@ -340,7 +342,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 const int n1 = fwd_item_iters(rlo, rhi, bh_ / p.H, q0, 1, p.Sq, p.Sk, p.causal, jb_);
                 const int n = max(n0, n1);
                 // ---- S_t(0)
-                {
+                if (n > 0) {
                     const uint32_t st = kv_cnt % C::kStages;
                     kv_wait(kv_cnt);
                     if (n0 > 0) {
@@ -418,11 +420,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             int jb;
             const int nt = fwd_item_iters(rlo, rhi, bh / p.H, q0, t, p.Sq, p.Sk, p.causal, jb);
             const int n_rounds = max(nt, fwd_item_iters(rlo, rhi, bh / p.H, q0, 1 - t, p.Sq, p.Sk, p.causal, jb));
+            const int row_g = q0 + t * 128 + r;
             if (nt == 0) {
                 if (FA_FWD_STAGGER) for (int j = 0; j < n_rounds; ++j) { named_bar_sync(3 + t, 256); named_bar_arrive(4 - t, 256); }
+                if constexpr (kRanges) {
+                    if (q0 + t * 128 < p.Sq) {             // rows whose key range is empty: O = 0, LSE = -inf (the outputs are torch.empty)
+                        #pragma unroll
+                        for (int g = 0; g < 8; ++g) sts128(smem_u32(sOt) + sw128_offset(r, g), 0u, 0u, 0u, 0u);
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + t, 128);
+                        if (r == 0) {
+                            #pragma unroll
+                            for (int c = 0; c < C::kChunks; ++c) tma_store_4d(&mapO, sOt, c * 64, q0 + t * 128, bh % p.H, bh / p.H);
+                            tma_store_commit();
+                            tma_store_wait_read0();
+                        }
+                        named_bar_sync(1 + t, 128);
+                        if (row_g < p.Sq) p.lse[(size_t)bh * p.Sq + row_g] = -INFINITY;
+                    }
+                }
                 continue;
             }
-            const int row_g = q0 + t * 128 + r;
             int k_lo = 0, k_hi = p.Sk;                    // keys this row may see (before the causal clip)
             if constexpr (kRanges) {
                 const size_t ri = (size_t)(bh / p.H) * p.Sq + min(row_g, p.Sq - 1);
@@ -561,6 +579,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem, 512);
+    hang_trap_if_set();
 }
 
 }  // namespace fa

@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
 #include <utility>
 
 namespace fa {
@@ -70,12 +71,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must never hang the GPU box.  After ~4 s without progress the first
-// waiter records who it is and sets g_hang_flag; every waiter then abandons its wait, so the kernel
-// drains (with garbage results) and the host can read the record (fa_sm100_last_hang) instead of
-// facing a dead context.
+// Bounded wait: a protocol bug must never hang the GPU box.  After FA_WAIT_TIMEOUT_NS without progress the first waiter records who
+// it is in g_hang_record / g_hang_flag; every waiter then abandons its wait, the kernel drains and TRAPS at its end
+// (hang_trap_if_set): the launch fails with a sticky CUDA error, so this and every later call of the process report it instead of
+// handing back garbage.  The timeout is wall clock (globaltimer keeps running under time-slicing or a debugger), hence generous.
+// Development builds (-DFA_HANG_TRAP=0) do not trap: the kernel finishes with garbage results and fa_sm100_last_hang() returns the
+// record.  (The trap sits at the kernel's end, not in the wait loop: inside the loop it changes the register allocation of every
+// hot loop that waits on a barrier.)
 #ifndef FA_WAIT_TIMEOUT_NS
-#define FA_WAIT_TIMEOUT_NS 4000000000ull
+#define FA_WAIT_TIMEOUT_NS 20000000000ull
+#endif
+#ifndef FA_HANG_TRAP
+#define FA_HANG_TRAP 1
 #endif
 __device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t tag) {
     uint64_t t0 = 0;
@@ -95,6 +102,10 @@ __device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, u
             }
         }
     }
+}
+// last statement of every kernel that waits on mbarriers
+__device__ __forceinline__ void hang_trap_if_set() {
+    if (FA_HANG_TRAP && threadIdx.x == 0 && *reinterpret_cast<volatile unsigned int*>(&g_hang_flag)) __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
     if (mbar_try_wait(bar, parity)) return;
@@ -461,6 +472,18 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = FA_PDL ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// The opt-in to > 48 KB of dynamic shared memory is a per-device (per-context) attribute of the kernel: set it once per device
+// ordinal, not once per process, or the first launch on a second GPU of the same process fails with "invalid value".
+template <auto Kernel>
+inline cudaError_t ensure_smem(int bytes, int dev) {
+    static std::atomic<unsigned long long> done{0};           // one bit per device ordinal (< 64, checked by the C API)
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
 }
 
 // register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it)

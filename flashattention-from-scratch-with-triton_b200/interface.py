@@ -28,6 +28,32 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+# Native host path (csrc/fa_torch.cpp -> _fa_torch.so): the same operator as FlashAttentionFunction below, as a C++ autograd node
+# over the same C ABI.  flash_attention() uses it for the plain operator (contiguous inputs, no range mask, no dropout): a short
+# step (C2: 0.2 ms of GPU work) otherwise spends a comparable time in Python autograd + ctypes marshalling, which is what limited
+# the 8-rank run.  FA_SM100_HOST=python selects the Python class everywhere (A/B, debugging).  Neither is a
+# fallback for the other's kernels: both launch libfa_sm100.so, and a missing _fa_torch.so is an ImportError.
+_HOST_NATIVE = os.environ.get("FA_SM100_HOST", "native") != "python"
+_native = None
+
+
+def _load_native():
+    global _native
+    if _native is None:
+        import importlib.util
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_fa_torch.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} not found: build it with `python flashattention-from-scratch-with-triton_b200/build.py` "
+                              "(g++ against the torch headers), or set FA_SM100_HOST=python for the Python host path")
+        _cabi.load()                                       # the library the extension links to (same file, loaded once)
+        spec = importlib.util.spec_from_file_location("_fa_torch", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.set_deterministic(_deterministic)
+        _native = mod
+    return _native
+
+
 class _on_device:
     """torch.cuda.device(d) as a context only when d is not already current: the context manager costs ~10 us per call,
     comparable to the whole launch path, and a short step (C2: 0.2 ms on the GPU) must not become host-bound."""
@@ -86,13 +112,41 @@ class Ranges:
 
     @staticmethod
     def from_cu_seqlens(cu_seqlens, total=None, device=None):
-        """Packed self-attention (Phase_6.md:160-174): tokens [cu[s], cu[s+1]) form sequence s and attend only inside it."""
+        """Packed self-attention (Phase_6.md:160-174): tokens [cu[s], cu[s+1]) form sequence s and attend only inside it.
+        A packed buffer longer than cu[-1] (a padded tail) is handled by treating the pad tokens [cu[-1], total) as one more
+        sequence: the row side and the key side then describe the SAME mask, no real token ever sees a pad token, and the
+        pad rows' outputs / gradients depend on pad data only."""
         cu = torch.as_tensor(cu_seqlens, dtype=torch.int64, device=device)
-        total = int(cu[-1]) if total is None else total
+        last = int(cu[-1])
+        total = last if total is None else int(total)
+        assert total >= last, f"packed buffer of {total} tokens is shorter than cu_seqlens[-1] = {last}"
+        if total > last:
+            cu = torch.cat([cu, torch.tensor([total], dtype=torch.int64, device=cu.device)])
         pos = torch.arange(total, device=cu.device)
         sid = torch.searchsorted(cu[1:].contiguous(), pos, right=True).clamp_(max=cu.numel() - 2)
         lo, hi = cu[sid][None], cu[sid + 1][None]
         return Ranges(lo, hi, lo, hi)
+
+    def validate(self, is_causal=False):
+        """Check the documented preconditions (include/fa_sm100.h): all four arrays non-decreasing along the sequence,
+        lo <= hi, and the row side and the key side describing the same mask (query i sees key j  <=>  key j is seen by
+        query i).  O(B*Sq*Sk) memory: a debugging aid for hand-built masks, not part of the hot path.  Rows with an empty
+        range are legal (O = 0, LSE = -inf, zero gradients)."""
+        rl, rh, cl, ch = (t.long() for t in (self.row_lo, self.row_hi, self.col_lo, self.col_hi))
+        for name, t in (("row_lo", rl), ("row_hi", rh), ("col_lo", cl), ("col_hi", ch)):
+            if t.shape[1] > 1 and bool((t[:, 1:] < t[:, :-1]).any()):
+                raise ValueError(f"Ranges.{name} must be non-decreasing along the sequence")
+        if bool((rl > rh).any()) or bool((cl > ch).any()):
+            raise ValueError("Ranges: lo must not exceed hi")
+        Sq, Sk = rl.shape[1], cl.shape[1]
+        i = torch.arange(Sq, device=rl.device)[None, :, None]; j = torch.arange(Sk, device=rl.device)[None, None, :]
+        row_view = (j >= rl[:, :, None]) & (j < rh[:, :, None].clamp(max=Sk))
+        col_view = (i >= cl[:, None, :]) & (i < ch[:, None, :].clamp(max=Sq))
+        if is_causal:
+            row_view &= (j <= i); col_view &= (j <= i)
+        if not torch.equal(row_view, col_view):
+            raise ValueError("Ranges: row_lo/row_hi and col_lo/col_hi describe different masks")
+        return self
 
     @staticmethod
     def from_key_padding(seqlens_k, S_q, S_k, device=None):
@@ -191,6 +245,8 @@ def set_deterministic(flag: bool) -> bool:
     """Select the bitwise-reproducible two-kernel backward for every head dim; returns the previous setting."""
     global _deterministic
     prev, _deterministic = _deterministic, bool(flag)
+    if _native is not None:
+        _native.set_deterministic(_deterministic)
     return prev
 
 
@@ -276,6 +332,16 @@ def flash_attention(Q, K, V, is_causal=False, *, sm_scale=None, ranges=None, dro
     ``ranges`` (a Ranges object) adds a per-row key-range mask: packed sequences, key padding, sliding windows.
     ``dropout_p`` > 0 drops attention probabilities (quantised to 1/256, kept ones scaled by 1/(1-p)); the mask is a pure
     function of ``dropout_seed`` (drawn from torch's CPU generator when None) and the element's coordinates."""
+    if _HOST_NATIVE and ranges is None and not dropout_p:
+        # the reference's asserts (:133-136), then the C++ autograd node when the layout needs no tensor-map strides
+        assert Q.is_cuda and K.is_cuda and V.is_cuda
+        assert Q.dtype in (torch.float16, torch.bfloat16)
+        assert Q.shape[-1] == K.shape[-1] == V.shape[-1]
+        assert Q.ndim == 4 and K.ndim == 4 and V.ndim == 4
+        assert K.dtype == Q.dtype and V.dtype == Q.dtype
+        assert K.shape[:3] == V.shape[:3] and K.shape[0] == Q.shape[0] and Q.shape[1] % K.shape[1] == 0
+        if Q.is_contiguous() and K.is_contiguous() and V.is_contiguous():
+            return (_native or _load_native()).flash_attention(Q, K, V, bool(is_causal), float(sm_scale) if sm_scale is not None else 0.0)
     if dropout_p and dropout_seed is None:
         dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     return FlashAttentionFunction.apply(Q, K, V, is_causal, sm_scale, ranges, float(dropout_p or 0.0), dropout_seed or 0)

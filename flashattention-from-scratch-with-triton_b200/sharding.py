@@ -113,130 +113,235 @@ class CudaOps:
         return dq, dk, dv
 
 
-def _exchange(send: List[torch.Tensor], recv: List[torch.Tensor], group, rank: int, world: int):
-    """Post send-to-next / recv-from-prev for a list of tensors; returns the requests."""
-    import torch.distributed as dist
-    nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
-    prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world
-    ops = []
-    for s, r in zip(send, recv):
-        ops.append(dist.P2POp(dist.isend, s, nxt, group))
-        ops.append(dist.P2POp(dist.irecv, r, prv, group))
-    return dist.batch_isend_irecv(ops)
+class DistComm:
+    """Ring neighbours over ``torch.distributed`` point-to-point ops (NCCL over NVLink on GPUs, gloo on CPU ranks)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group); self.rank = dist.get_rank(group)
+        g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        self.nxt, self.prv = g((self.rank + 1) % self.world), g((self.rank - 1) % self.world)
+
+    def exchange(self, send: List[torch.Tensor], recv: List[torch.Tensor]):
+        """Post send-to-next / recv-from-prev for a list of tensors; returns an object with .wait()."""
+        import torch.distributed as dist
+        ops = []
+        for s, r in zip(send, recv):
+            ops.append(dist.P2POp(dist.isend, s, self.nxt, self.group))
+            ops.append(dist.P2POp(dist.irecv, r, self.prv, self.group))
+        return _Pending(dist.batch_isend_irecv(ops))
+
+
+class _Pending:
+    def __init__(self, reqs):
+        self.reqs = reqs
+
+    def wait(self):
+        for r in self.reqs:
+            r.wait()
+
+
+def _parts(B: int, Hk: int, G: int, n: int):
+    """Cut one hop's work into <= n independent sub-launches: along the batch if B > 1, else along the K/V heads (slices of a
+    contiguous [B,H,S,D] tensor that are contiguous themselves).  Yields (q-side index, kv-side index) tuples."""
+    if B > 1:
+        n = max(1, min(n, B)); per = -(-B // n)
+        return [((slice(b, min(b + per, B)),), (slice(b, min(b + per, B)),)) for b in range(0, B, per)]
+    n = max(1, min(n, Hk)); per = -(-Hk // n)
+    return [((slice(None), slice(h * G, min(h + per, Hk) * G)), (slice(None), slice(h, min(h + per, Hk)))) for h in range(0, Hk, per)]
+
+
+def _mark(timeline, t, name):
+    """Optional per-hop timeline: CUDA events on the current stream (GPU tensors only)."""
+    if timeline is not None and t.is_cuda:
+        ev = torch.cuda.Event(enable_timing=True); ev.record()
+        timeline.append((name, ev))
 
 
 # ------------------------------------------------------------------------------------------------
 # ring forward / backward
 # ------------------------------------------------------------------------------------------------
+# Why a hop is cut into sub-launches (`splits`): the attention kernels are persistent, one CTA per SM using the SM's whole
+# register file, so while one of them runs NOTHING else can be scheduled on the GPU — including NCCL's send/recv kernels.  A hop
+# issued as one launch therefore serialises "transfer" and "compute" no matter which stream they are on.  Cut into a few
+# launches (by K/V head or batch: independent problems), the SMs change hands at every boundary and the pending NCCL kernel gets
+# its CTAs; the dynamic tile scheduler of the next launch simply runs on the SMs that are left.
 
 
-def ring_attention_forward(q, k, v, group=None, ops=None):
+def ring_attention_forward(q, k, v, group=None, ops=None, comm=None, splits=None, timeline=None):
     """Causal attention over the global sequence; q,k,v are this rank's zigzag-local [B,H,2c,D] tensors.
     Returns (O [B,H,2c,D] in q.dtype, LSE [B,H,2c] fp32) for the local rows."""
-    import torch.distributed as dist
     ops = ops or CudaOps()
-    world = dist.get_world_size(group); rank = dist.get_rank(group)
+    comm = comm or DistComm(group)
+    world, rank = comm.world, comm.rank
     B, H, S2, D = q.shape
+    Hk = k.shape[1]; G = H // Hk
     c = S2 // 2
-    O_acc = torch.zeros(B, H, S2, D, dtype=torch.float32, device=q.device)
-    L_acc = torch.full((B, H, S2), float("-inf"), dtype=torch.float32, device=q.device)
-    q_hi = q[:, :, c:].contiguous()
-    kv = [k.contiguous(), v.contiguous()]
+    parts = _parts(B, Hk, G, splits if splits is not None else (4 if world > 1 else 1))
+    O_acc = torch.empty(B, H, S2, D, dtype=torch.float32, device=q.device)
+    L_acc = torch.empty((B, H, S2), dtype=torch.float32, device=q.device)
+    q = q.contiguous()
+    cur = [k.contiguous(), v.contiguous()]
+    # two receive buffers per tensor, allocated once: hop s computes on `cur` while the block of hop s+1 lands in bufs[s % 2]
+    bufs = [[torch.empty_like(cur[0]), torch.empty_like(cur[1])] for _ in range(min(2, world - 1))]
     for s in range(world):
-        reqs, nxt = [], None
+        _mark(timeline, q, f"fwd{s}:start")
+        pending, nxt = None, None
         if s + 1 < world:                                     # prefetch the next visiting block under this hop's compute
-            nxt = [torch.empty_like(kv[0]), torch.empty_like(kv[1])]
-            reqs = _exchange(kv, nxt, group, rank, world)
+            nxt = bufs[s % 2]
+            pending = comm.exchange(cur, nxt)
         o = (rank - s) % world                                # owner of the visiting K/V block
-        if o == rank:
-            Op, Lp = ops.fwd(q, kv[0], kv[1], True)
-            ops.merge_(O_acc, L_acc, Op, Lp, 0)
-        elif o < rank:
-            Op, Lp = ops.fwd(q, kv[0][:, :, :c].contiguous(), kv[1][:, :, :c].contiguous(), False)
-            ops.merge_(O_acc, L_acc, Op, Lp, 0)
-        else:
-            Op, Lp = ops.fwd(q_hi, kv[0], kv[1], False)
-            ops.merge_(O_acc, L_acc, Op, Lp, c)
-        for r in reqs:
-            r.wait()
-        if nxt is not None:
-            kv = nxt
+        for qi, ki in parts:
+            if o == rank:                                     # always hop 0: the accumulators start from this partial
+                Op, Lp = ops.fwd(q[qi], cur[0][ki], cur[1][ki], True)
+                O_acc[qi].copy_(Op); L_acc[qi].copy_(Lp)
+            elif o < rank:                                    # all local queries x first half of the visiting block (strided view)
+                Op, Lp = ops.fwd(q[qi], cur[0][ki][:, :, :c], cur[1][ki][:, :, :c], False)
+                ops.merge_(O_acc[qi], L_acc[qi], Op, Lp, 0)
+            else:                                             # second half of the local queries x the whole visiting block
+                Op, Lp = ops.fwd(q[qi][:, :, c:], cur[0][ki], cur[1][ki], False)
+                ops.merge_(O_acc[qi], L_acc[qi], Op, Lp, c)
+        _mark(timeline, q, f"fwd{s}:compute_end")
+        if pending is not None:
+            pending.wait()
+            cur = nxt
+        _mark(timeline, q, f"fwd{s}:end")
     return O_acc.to(q.dtype), L_acc
 
 
-def ring_attention_backward(q, k, v, O, dO, LSE, group=None, ops=None):
+def ring_attention_backward(q, k, v, O, dO, LSE, group=None, ops=None, comm=None, splits=None, timeline=None):
     """Gradients for ring_attention_forward.  Returns (dq, dk, dv) for the local rows, in q.dtype.
 
     Two rings run under the compute: the K/V block of the next hop is prefetched while the current hop's
     kernels run, and the fp32 dK/dV accumulators of the block that just left are in flight to the next rank
-    while this rank already computes its contribution to the following block; they are added on arrival."""
-    import torch.distributed as dist
+    while this rank already computes its contribution to the following block; they are added on arrival.
+    All ring buffers are allocated once (two K/V receive buffers, two accumulator pairs)."""
     ops = ops or CudaOps()
-    world = dist.get_world_size(group); rank = dist.get_rank(group)
+    comm = comm or DistComm(group)
+    world, rank = comm.world, comm.rank
     B, H, S2, D = q.shape
+    Hk = k.shape[1]; G = H // Hk
     c = S2 // 2
+    parts = _parts(B, Hk, G, splits if splits is not None else (4 if world > 1 else 1))
     f32 = dict(dtype=torch.float32, device=q.device)
-    delta = ops.delta(O.contiguous(), dO.contiguous())        # global: uses the final O of the local rows
+    q, O, dO, LSE = q.contiguous(), O.contiguous(), dO.contiguous(), LSE.contiguous()
+    delta = ops.delta(O, dO)                                  # global: uses the final O of the local rows
+    L_hi, d_hi = LSE[:, :, c:].contiguous(), delta[:, :, c:].contiguous()   # the C ABI wants contiguous fp32 statistics
     dq_acc = torch.zeros(B, H, S2, D, **f32)
-    hi = lambda t: t[:, :, c:].contiguous()
-    q_hi, O_hi, dO_hi, L_hi, d_hi = hi(q), hi(O), hi(dO), hi(LSE), hi(delta)
-    kv = [k.contiguous(), v.contiguous()]
-    dkv = [torch.zeros(B, H, S2, D, **f32), torch.zeros(B, H, S2, D, **f32)]   # accumulators of the visiting block
-    dkv_reqs, dkv_in = [], None
+    cur = [k.contiguous(), v.contiguous()]
+    bufs = [[torch.empty_like(cur[0]), torch.empty_like(cur[1])] for _ in range(min(2, world - 1))]
+    acc = [torch.zeros(B, Hk, S2, D, **f32), torch.zeros(B, Hk, S2, D, **f32)]   # accumulators of the visiting block
+    acc_in = [torch.empty_like(acc[0]), torch.empty_like(acc[1])] if world > 1 else None
+    acc_pending = None
     for s in range(world):
-        kv_reqs, nxt = [], None
+        _mark(timeline, q, f"bwd{s}:start")
+        kv_pending, nxt = None, None
         if s + 1 < world:
-            nxt = [torch.empty_like(kv[0]), torch.empty_like(kv[1])]
-            kv_reqs = _exchange(kv, nxt, group, rank, world)
+            nxt = bufs[s % 2]
+            kv_pending = comm.exchange(cur, nxt)
         o = (rank - s) % world
-        if o == rank:
-            dq, dk, dv = ops.bwd(q, kv[0], kv[1], O, dO, LSE, delta, True)
-            part = (slice(None), slice(None), slice(0, S2))
-            dq_acc.add_(dq)
-        elif o < rank:
-            dq, dk, dv = ops.bwd(q, kv[0][:, :, :c].contiguous(), kv[1][:, :, :c].contiguous(), O, dO, LSE, delta, False)
-            part = (slice(None), slice(None), slice(0, c))
-            dq_acc.add_(dq)
-        else:
-            dq, dk, dv = ops.bwd(q_hi, kv[0], kv[1], O_hi, dO_hi, L_hi, d_hi, False)
-            part = (slice(None), slice(None), slice(0, S2))
-            dq_acc[:, :, c:].add_(dq)
-        if s > 0:                                             # accumulators of this block, sent by the previous rank
-            for r in dkv_reqs:
-                r.wait()
-            dkv = dkv_in
-        dkv[0][part].add_(dk); dkv[1][part].add_(dv)
-        # pass them on with their block (after the last hop they arrive back at the block's owner)
-        dkv_in = [torch.empty_like(dkv[0]), torch.empty_like(dkv[1])]
-        dkv_reqs = _exchange(dkv, dkv_in, group, rank, world)
-        for r in kv_reqs:
-            r.wait()
-        if nxt is not None:
-            kv = nxt
-    for r in dkv_reqs:
-        r.wait()
-    return dq_acc.to(q.dtype), dkv_in[0].to(q.dtype), dkv_in[1].to(q.dtype)
+        grads = []
+        for qi, ki in parts:
+            if o == rank:
+                dq, dk, dv = ops.bwd(q[qi], cur[0][ki], cur[1][ki], O[qi], dO[qi], LSE[qi], delta[qi], True)
+                dq_acc[qi].add_(dq); rows = slice(0, S2)
+            elif o < rank:
+                dq, dk, dv = ops.bwd(q[qi], cur[0][ki][:, :, :c], cur[1][ki][:, :, :c], O[qi], dO[qi], LSE[qi], delta[qi], False)
+                dq_acc[qi].add_(dq); rows = slice(0, c)
+            else:
+                hi = lambda t: t[qi][:, :, c:]
+                dq, dk, dv = ops.bwd(hi(q), cur[0][ki], cur[1][ki], hi(O), hi(dO), L_hi[qi], d_hi[qi], False)
+                dq_acc[qi][:, :, c:].add_(dq); rows = slice(0, S2)
+            grads.append((ki, rows, dk, dv))
+        _mark(timeline, q, f"bwd{s}:compute_end")
+        if acc_pending is not None:                           # accumulators of this block, sent by the previous rank last hop
+            acc_pending.wait()
+            acc, acc_in = acc_in, acc
+        for ki, rows, dk, dv in grads:
+            acc[0][ki][:, :, rows].add_(dk); acc[1][ki][:, :, rows].add_(dv)
+        if world > 1:                                         # pass them on with their block (the last hop brings them home)
+            acc_pending = comm.exchange(acc, acc_in)
+        if kv_pending is not None:
+            kv_pending.wait()
+            cur = nxt
+        _mark(timeline, q, f"bwd{s}:end")
+    if acc_pending is not None:
+        acc_pending.wait()
+        acc = acc_in
+    return dq_acc.to(q.dtype), acc[0].to(q.dtype), acc[1].to(q.dtype)
 
 
 class RingFlashAttentionFunction(torch.autograd.Function):
     """Autograd wrapper with the same saved-tensor contract as FlashAttentionFunction (Q,K,V,O,LSE)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, group=None):
+    def forward(ctx, q, k, v, group=None, comm=None, splits=None, timeline=None):
         assert q.dtype in (torch.float16, torch.bfloat16) and q.ndim == 4
         q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
-        O, LSE = ring_attention_forward(q_, k_, v_, group)
+        O, LSE = ring_attention_forward(q_, k_, v_, group, None, comm, splits, timeline)
         ctx.save_for_backward(q_, k_, v_, O, LSE)
-        ctx.group = group
+        ctx.ring = (group, comm, splits, timeline)
         return O
 
     @staticmethod
     def backward(ctx, dO):
         q, k, v, O, LSE = ctx.saved_tensors
-        dq, dk, dv = ring_attention_backward(q, k, v, O, dO.contiguous(), LSE, ctx.group)
-        return dq, dk, dv, None
+        group, comm, splits, timeline = ctx.ring
+        dq, dk, dv = ring_attention_backward(q, k, v, O, dO.contiguous(), LSE, group, None, comm, splits, timeline)
+        return dq, dk, dv, None, None, None, None
 
 
-def ring_flash_attention(q, k, v, group=None):
-    """Causal attention over a sequence sharded zigzag-wise across the ranks of `group`."""
-    return RingFlashAttentionFunction.apply(q, k, v, group)
+def ring_flash_attention(q, k, v, group=None, comm=None, splits=None, timeline=None):
+    """Causal attention over a sequence sharded zigzag-wise across the ranks of `group` (or of an injected `comm`)."""
+    return RingFlashAttentionFunction.apply(q, k, v, group, comm, splits, timeline)
+
+
+class ThreadRingComm:
+    """In-process ring for P simulated ranks, one Python thread each, all on ONE device and one CUDA stream: the ring schedule
+    and the real local kernels can be verified on a single GPU (tests/) or on CPU tensors.  exchange() snapshots the send
+    buffers (a buffered send) and hands them to the next rank's queue; wait() copies the previous rank's snapshot into the
+    receive buffers.  Stream order makes the data dependencies safe: a snapshot is enqueued after its producers and the copy
+    after the snapshot, all on the same stream."""
+
+    def __init__(self, rank, world, queues):
+        self.rank, self.world, self.queues = rank, world, queues
+
+    @staticmethod
+    def make(world):
+        import queue
+        qs = [queue.Queue() for _ in range(world)]            # qs[r]: messages for rank r (from r - 1)
+        return [ThreadRingComm(r, world, qs) for r in range(world)]
+
+    def exchange(self, send, recv):
+        self.queues[(self.rank + 1) % self.world].put([t.clone() for t in send])
+        comm = self
+
+        class _P:
+            def wait(self_inner):
+                got = comm.queues[comm.rank].get(timeout=600)
+                for dst, src in zip(recv, got):
+                    dst.copy_(src)
+        return _P()
+
+
+def run_virtual_ring(world, fn):
+    """Run fn(rank, comm) on `world` threads sharing a ThreadRingComm ring; returns the list of results (exceptions re-raised)."""
+    import threading
+    comms = ThreadRingComm.make(world)
+    out, err = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            out[r] = fn(r, comms[r])
+        except BaseException as e:   # noqa: BLE001 - re-raised in the caller
+            err[r] = e
+    ths = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out

@@ -76,6 +76,26 @@ def test_zigzag_ring_fwd_bwd_equals_full_causal_attention(world):
             assert max(ret[r]) < 2e-5, (r, ret[r])
 
 
+@pytest.mark.parametrize("world,splits", [(2, 1), (4, 2), (8, 3)])
+def test_virtual_ring_threads_equals_full_causal_attention(world, splits):
+    """The same ring code driven by ThreadRingComm (P simulated ranks as threads of ONE process — the harness the GPU test
+    uses with the CUDA kernels), with sub-launch splitting, against the fp64 closed form."""
+    S = 32 * world
+    Q, K, V, dO = orc.make_inputs(2 if world == 4 else 1, 3, S, S, 64, torch.float32, seed=9)
+    rO, rLSE, rdQ, rdK, rdV = orc.closed_form(Q, K, V, dO, True, dtype=torch.float64)
+
+    def rank_fn(rank, comm):
+        q, k, v, do = (sh.zigzag_split(t, rank, world) for t in (Q, K, V, dO))
+        ops = OracleOps()
+        O, LSE = sh.ring_attention_forward(q, k, v, None, ops, comm, splits)
+        return (O, LSE) + tuple(sh.ring_attention_backward(q, k, v, O, do, LSE, None, ops, comm, splits))
+
+    outs = sh.run_virtual_ring(world, rank_fn)
+    for i, ref in enumerate((rO, rLSE, rdQ, rdK, rdV)):
+        full = sh.zigzag_merge([o[i] for o in outs], dim=2)
+        assert (full - ref.float()).abs().max() < 2e-5, i
+
+
 def _shard_worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
