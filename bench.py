@@ -1,26 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: flash_attention forward + backward on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4s|C4|sweep4k] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C2|C3|C4s|sweep4k] [--impl ours|reference]
 
-A "step" is one fwd+bwd pass of the operator over one batch of synthetic [B,H,S,D] inputs (the
-reference's own benchmark step, code/Performance_Comparison.py:66-76).  Metric and FLOP model are the
-reference's: TFLOPS = 3.5 * 4*B*H*Sq*Sk*D/(2 if causal) / t  (code/Performance_Comparison.py:99-107).
+A "step" is one fwd+bwd pass of the operator over one batch of synthetic [B,H,S,D] inputs through the autograd entry (the
+reference's own benchmark step, code/Performance_Comparison.py:66-76).  Metric and FLOP model are the reference's:
+TFLOPS = 3.5 * 4*B*H*Sq*Sk*D/(2 if causal) / t  (code/Performance_Comparison.py:99-107).
 
-N=1 workload: BASELINE.json configs[1] (C2: B=4 H=16 N=2048 D=64 bf16 causal fwd+bwd).  N>1: batch x head
-sharding — every rank runs the same per-GPU shard shape on its own synthetic batch (global batch = N*B),
-no data-path collective => "scaling": "weak"; `value` is the aggregate over all ranks and the
-time is the max over ranks.
+Headline workload (every N): BASELINE.json configs[3] = C4, B=16 H=32 N=8192 D=128 bf16 causal — the config the north star's
+D=128 targets and "near-linear 8-GPU scaling" are written for.  It fits one GPU (8 tensors x 1 GiB).  N GPUs: batch x head
+sharding, rank r takes B/N of the batch, NO data-path collective => "scaling": "strong"; `value` = FLOPs of the
+whole C4 problem / max-over-ranks step time.  `--workload C2|C3|C4s` keeps the round-1 behaviour (that shape on every rank).
 
 One JSON line on stdout (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (the backward kernel) against the MEASURED dense-bf16 peak
-  kernels       per-kernel ms / algorithmic TFLOP/s / fraction (fwd, delta, fused + convert at D=64 | dQ, dKV), timed individually
-  cpu_baseline  the CPU ground-truth path (PyTorch SDPA on the host cores) on the same workload
+  roofline      the backward (delta + dQ + dK/dV kernels, the dominant 70 % of the step) with ALGORITHMIC FLOPs (2.5 x forward
+                FLOPs) against the measured dense-bf16 peak; `mma_utilisation` = executed GEMM FLOPs (7 units) instead
+  kernels       per-kernel ms / TFLOP/s (algorithmic and executed) / fraction, each timed alone with CUDA events
+  cpu_baseline  the CPU ground-truth path (PyTorch SDPA on the host cores) on a bounded sample of the same workload
   e2e           same metric with pinned-host inputs and outputs, H2D/D2H copies inside the timed region
-  also          kernel-level numbers of the D=128 configs (C3 and one 8-GPU shard of C4), untimed extras
-`--impl reference` runs the reference's own Triton kernels (baseline/_ref, unmodified, fp16 — the shipped
-kernels assert on bf16) on the same GPU through the reference's public API; if that copy or Triton is not
-usable it times the CPU ground-truth path instead and says so.
+  also          C2 and C3 through the same autograd entry with ms_per_step (L2 flushed), per rank, + host time per step
+  ring          (N >= 2) C5: B=1 H=32 N=131072 D=128 causal, sequence-sharded zigzag ring over NCCL P2P, per-hop timeline
+`--impl reference` runs the reference's own Triton kernels (baseline/_ref, unmodified, fp16 — the shipped kernels assert on
+bf16) on the same GPU(s) through the reference's public API; if that copy or Triton is not usable it times the CPU ground-truth
+path instead and says so.
 """
 from __future__ import annotations
 
@@ -42,9 +44,10 @@ WORKLOADS = {
     "C2": (4, 16, 2048, 64, True),
     "C3": (4, 16, 4096, 128, False),
     "C4s": (2, 32, 8192, 128, True),       # one 8-GPU shard of C4 (B = 16/8)
-    "C4": (16, 32, 8192, 128, True),
+    "C4": (16, 32, 8192, 128, True),       # strong-scaled over --gpus: B = 16/N per rank
     "sweep4k": (4, 8, 4096, 128, True),    # code/Performance_Comparison.py:152-162
 }
+C5 = (1, 32, 131072, 128)                  # ring block: B, H, N, D (causal)
 
 
 def _peaks():
@@ -57,7 +60,7 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
@@ -67,17 +70,20 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def n_lines(self):
+        return len(self.lines)
+
+    def stop(self, window):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.25)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -101,8 +107,7 @@ class ClockSampler:
                         reasons.add(name)
         sm = sorted(sm_load or sm_all)
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm_all), samples_under_load=len(sm_load),
-                    window="1.5 s loop of the same step right after the timed region (100 ms period; median over samples with GPU utilisation >= 50 %)")
+                    samples=len(sm_all), samples_under_load=len(sm_load), window=window)
 
 
 def cpu_baseline(B, H, S, D, causal, budget_s=20.0):
@@ -114,7 +119,7 @@ def cpu_baseline(B, H, S, D, causal, budget_s=20.0):
     bh_total = B * H
     Q, K, V, dO = orc.make_inputs(1, 1, S, S, D, torch.float32, seed=0)
     t0 = time.perf_counter(); orc.sdpa_cpu_flash(Q, K, V, dO, causal); t1 = time.perf_counter() - t0   # also warm-up
-    n = int(max(1, min(bh_total, budget_s / max(t1, 1e-4))))
+    n = int(max(1, min(bh_total, 0.5 * budget_s / max(t1, 1e-4), 4 * nthreads)))
     Q, K, V, dO = orc.make_inputs(1, n, S, S, D, torch.float32, seed=0)
     best = float("inf")
     for _ in range(2):
@@ -126,15 +131,18 @@ def cpu_baseline(B, H, S, D, causal, budget_s=20.0):
                 seconds=best)
 
 
-def time_steps(step_fn, steps, warmup, flush):
-    """Each step timed with its own CUDA-event pair on the current stream; L2 flushed between steps."""
+def time_steps(step_fn, steps, warmup, flush=None):
+    """Each step timed with its own CUDA-event pair on the current stream; L2 flushed between steps when `flush` is given."""
     import torch
     for _ in range(warmup):
-        flush.zero_(); step_fn()
+        if flush is not None:
+            flush.zero_()
+        step_fn()
     torch.cuda.synchronize()
     evs = []
     for _ in range(steps):
-        flush.zero_()
+        if flush is not None:
+            flush.zero_()
         s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
         s.record(); step_fn(); e.record()
         evs.append((s, e))
@@ -145,14 +153,19 @@ def time_steps(step_fn, steps, warmup, flush):
 def make_inputs(B, H, S, D, dtype, seed, device):
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
-    return tuple(torch.randn(B, H, S, D, device=device, generator=g, dtype=torch.float32).to(dtype) for _ in range(4))
+    out = []
+    for _ in range(4):                               # fp32 draw cast to the run dtype, one (b) slab at a time
+        t = torch.empty(B, H, S, D, device=device, dtype=dtype)
+        for b in range(B):
+            t[b] = torch.randn(H, S, D, device=device, generator=g, dtype=torch.float32).to(dtype)
+        out.append(t)
+    return tuple(out)
 
 
 def kernel_breakdown(fa, Q, K, V, dO, causal, steps, warmup, flush, peak):
-    """Per-kernel CUDA-event timing through the C ABI.  Algorithmic FLOPs per launch = GEMM count of the
-    kernel's algorithm (fwd 2, dQ 3, dKV 4, fused dK/dV/dQ 5) x 2*B*H*Sq*Sk*D/(2 if causal).
-    Head dim 64 runs the fused backward (delta+zeroing, fused, conversion); the two-kernel backward of the
-    deterministic mode is timed beside it."""
+    """Per-kernel CUDA-event timing through the C ABI, each kernel alone.  `achieved` uses the kernel's ALGORITHMIC FLOPs; for the
+    backward kernels that is their share of the metric's 2.5 x forward FLOPs (the two-kernel backward executes 7 GEMM-units for
+    the 5 the metric counts: dQ 3, dK/dV 4), `executed` is the GEMM work actually issued."""
     import torch
     B, H, S, D = Q.shape
     O, LSE = fa.flash_attention_forward(Q, K, V, causal)
@@ -163,26 +176,38 @@ def kernel_breakdown(fa, Q, K, V, dO, causal, steps, warmup, flush, peak):
     T = Q.numel() * Q.element_size()
     two = lambda part: (lambda: fa.flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, causal, part))
     dbytes = 2 * T + B * H * S * 4                       # read O, dO; write delta
-    parts = {"fwd": (lambda: fa.flash_attention_forward(Q, K, V, causal), 2 * gemm, "tensor")}
+    # name: (launcher, executed GEMM units or bytes, bound)
+    parts = {"fwd": (lambda: fa.flash_attention_forward(Q, K, V, causal), 2, "tensor")}
     if D == 64 and not fa.is_deterministic():
         acc = torch.empty(B, H, S, D, dtype=torch.float32, device=Q.device)
         fus = lambda part: (lambda: fa.flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, causal, dq_acc=acc, parts=part))
         parts.update({"delta": (fus(1), dbytes + 2 * T, "hbm"),         # + zeros into the fp32 dQ workspace
-                      "fused": (fus(8), 5 * gemm, "tensor"),
+                      "fused": (fus(8), 5, "tensor"),
                       "convert": (fus(16), 3 * T, "hbm"),               # read fp32 workspace, write 16-bit dQ
-                      "two_kernel_dQ": (two(2), 3 * gemm, "tensor"), "two_kernel_dKV": (two(4), 4 * gemm, "tensor")})
+                      "two_kernel_dQ": (two(2), 3, "tensor"), "two_kernel_dKV": (two(4), 4, "tensor")})
+        bwd_names = ("delta", "fused", "convert")
     else:
-        parts.update({"delta": (two(1), dbytes, "hbm"), "dQ": (two(2), 3 * gemm, "tensor"), "dKV": (two(4), 4 * gemm, "tensor")})
+        parts.update({"delta": (two(1), dbytes, "hbm"), "dQ": (two(2), 3, "tensor"), "dKV": (two(4), 4, "tensor")})
+        bwd_names = ("delta", "dQ", "dKV")
     out = {}
-    for name, (fn, flops, bound) in parts.items():
+    for name, (fn, work, bound) in parts.items():
         ts = time_steps(fn, steps, warmup, flush)
         ms = sum(ts) / len(ts)
         if bound == "tensor":
-            ach = flops / (ms * 1e-3) / 1e12
-            out[name] = dict(ms=ms, bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peak["bf16_burst"])
+            ex = work * gemm / (ms * 1e-3) / 1e12
+            out[name] = dict(ms=ms, bound="tensor", executed_gemm_units=work, executed=ex, unit="TFLOP/s", executed_frac=ex / peak["bf16_burst"])
         else:
-            ach = flops / (ms * 1e-3) / 1e9              # bytes
+            ach = work / (ms * 1e-3) / 1e9               # bytes
             out[name] = dict(ms=ms, bound="hbm", achieved=ach, unit="GB/s", frac=ach / peak["hbm"])
+    # algorithmic view: forward = 2 GEMM-units; the whole backward (its kernels together) = 5 GEMM-units = 2.5 x forward FLOPs
+    out["fwd"].update(achieved=out["fwd"]["executed"], frac=out["fwd"]["executed_frac"])
+    t_bwd = sum(out[n]["ms"] for n in bwd_names)
+    ex_units = sum(out[n].get("executed_gemm_units", 0) for n in bwd_names)
+    alg = 5 * gemm / (t_bwd * 1e-3) / 1e12
+    out["backward"] = dict(ms=t_bwd, kernels=list(bwd_names), bound="tensor", achieved=alg, unit="TFLOP/s",
+                           frac=alg / peak["bf16_burst"], frac_of_sustained_peak=alg / peak["bf16_sustained"],
+                           algorithmic_flops=5 * gemm, executed_gemm_units=ex_units,
+                           mma_utilisation=ex_units * gemm / (t_bwd * 1e-3) / 1e12 / peak["bf16_burst"])
     return out
 
 
@@ -199,16 +224,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default=None, choices=[None, "bf16", "fp16"])
-    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / also / e2e (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / also / e2e / ring / kernels (profiling runs)")
+    ap.add_argument("--no-ring", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
     # libraries (NCCL's version banner, Triton autotune chatter) may print to fd 1: keep stdout for the ONE JSON line
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # ring: NCCL's P2P kernels get SMs first when a compute launch ends
     import torch
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -220,7 +247,14 @@ def main():
     if dist_on:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    B, H, S, D, causal = WORKLOADS[a.workload]
+    Bg, H, S, D, causal = WORKLOADS[a.workload]
+    strong = a.workload == "C4"
+    if strong:
+        if Bg % world:
+            raise SystemExit(f"C4 (B={Bg}) cannot be split over {world} ranks")
+        B = Bg // world
+    else:
+        B = Bg
     peak = _peaks()
 
     ref_note = None
@@ -237,10 +271,10 @@ def main():
         if why:
             # no usable copy of the reference kernels: time its CPU ground-truth path instead
             if rank == 0:
-                cb = cpu_baseline(B, H, S, D, causal)
+                cb = cpu_baseline(Bg, H, S, D, causal)
                 real_stdout.write(json.dumps({"impl": "reference", "metric": "fwd_bwd_tflops", "value": cb["value"], "unit": "TFLOPS",
                                   "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None,
-                                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                                  "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
                                   "data": "synthetic", "config": {"workload": a.workload, "note": f"reference Triton kernels unavailable ({why}); CPU ground-truth path timed"},
                                   "cpu_baseline": cb,
                                   "e2e": {"value": cb["value"], "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}) + "\n")
@@ -252,63 +286,126 @@ def main():
         lib = None
     dtype = torch.bfloat16 if dtype_name == "bf16" else torch.float16
 
-    Q, K, V, dO = make_inputs(B, H, S, D, dtype, seed=1234 + rank, device=dev)
-    Q.requires_grad_(True); K.requires_grad_(True); V.requires_grad_(True)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-
-    def step():
-        O = attn(Q, K, V, causal)
-        O.backward(dO)
-        Q.grad = None; K.grad = None; V.grad = None                   # code/Performance_Comparison.py:74-76
-        return O
-
     def barrier():
         if dist_on:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if not dist_on:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def autograd_step(Q, K, V, dO, c):
+        def step():
+            O = attn(Q, K, V, c)
+            O.backward(dO)
+            Q.grad = None; K.grad = None; V.grad = None               # code/Performance_Comparison.py:74-76
+            return O
+        return step
+
+    Q, K, V, dO = make_inputs(B, H, S, D, dtype, seed=1234 + rank, device=dev)
+    Q.requires_grad_(True); K.requires_grad_(True); V.requires_grad_(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    tensor_bytes = Q.numel() * Q.element_size()
+    main_flush = flush if 4 * tensor_bytes < (256 << 20) else None    # inputs far larger than L2 need no flush
+    step = autograd_step(Q, K, V, dO, causal)
+
     # ------------------------------- timed region: `value` -------------------------------
-    # Pre-warm: on a freshly acquired box the first process finds the GPU in a low-power state, and W = 10 steps of a 0.2 ms
-    # workload (2 ms) do not bring the clocks up — the same binary measured 382 and then 604 TFLOPS in two consecutive runs
-    # (profiles/r01_bench_cold_start.txt).  ~1 s of the same step, untimed, before the W warm-up steps; both arms do it.
+    # Pre-warm: on a freshly acquired box the first process finds the GPU in a low-power state (profiles/r01_bench_cold_start.txt);
+    # ~1 s of the same step, untimed, before the W warm-up steps; both arms do it.
     t_pre = time.time() + float(os.environ.get("FA_BENCH_PREWARM_S", "1.0"))
     while time.time() < t_pre:
-        for _ in range(20):
+        for _ in range(4):
             step()
         torch.cuda.synchronize()
     for _ in range(a.warmup):
-        flush.zero_(); step()
+        if main_flush is not None:
+            main_flush.zero_()
+        step()
     barrier()
     n0 = lib.fa_sm100_launch_count() if lib else 0
+    sampler = ClockSampler(local); sampler.start()
     barrier()
-    ts = time_steps(step, a.steps, 0, flush)
+    ts = time_steps(step, a.steps, 0, main_flush)
     barrier()
     launches = (lib.fa_sm100_launch_count() - n0) if lib else 0
-    # Clocks under load: the timed region of a small workload lasts only milliseconds, far below nvidia-smi's
-    # sampling period, so the SAME step is looped for ~1.5 s right after it while clocks / throttle reasons are sampled.
-    sampler = ClockSampler(local); sampler.start()
-    t_probe = time.time() + 1.5
-    while time.time() < t_probe:
-        for _ in range(20):
-            step()
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
-    my_ms = sum(ts) / len(ts)
-    ms = my_ms
-    if dist_on:
-        t = torch.tensor([my_ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
-    flops_step = 3.5 * 4 * B * H * S * S * D / (2 if causal else 1)
-    value = world * flops_step / (ms * 1e-3) / 1e12
+    # nvidia-smi needs a few 50 ms periods under load: a timed region shorter than that is extended by the SAME step, untimed
+    window = "sampled every 50 ms during the timed region"
+    if sum(ts) < 600.0:
+        t_probe = time.time() + 1.0
+        while time.time() < t_probe:
+            for _ in range(4):
+                step()
+            torch.cuda.synchronize()
+        window += " and a 1 s untimed loop of the same step right after it (the timed region is shorter than a few sampling periods)"
+    clocks = sampler.stop(window + "; median over samples with GPU utilisation >= 50 %")
+    ms = max_over_ranks(sum(ts) / len(ts))
+    flops_rank = 3.5 * 4 * B * H * S * S * D / (2 if causal else 1)
+    value = world * flops_rank / (ms * 1e-3) / 1e12
 
-    # ------------------------------- e2e: pinned host buffers in and out -------------------------------
-    e2e = None
+    line = {
+        "metric": "fwd_bwd_tflops", "value": value, "unit": "TFLOPS", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
+        "config": {"workload": (f"C4: B=16 H={H} N={S} D={D} causal fwd+bwd, batch x head sharded: B={B} per GPU" if strong else
+                                f"{a.workload}: B={B} H={H} N={S} D={D} {'causal' if causal else 'non-causal'} fwd+bwd per GPU"),
+                   "global_batch": B * world, "seq_len": S, "parallelism": f"batch x head sharding x{world}, no collective",
+                   "timing": "CUDA events per step on the launch stream through the autograd entry, max over ranks of the per-rank mean; "
+                             + ("inputs (4 x %d MiB per rank) are larger than the 126 MB L2, no flush" % (tensor_bytes >> 20) if main_flush is None
+                                else "L2 flushed (256 MiB write) between steps")
+                             + "; ~1 s of untimed pre-warm steps (clock ramp on a fresh box) before the W warm-up steps",
+                   "flop_model": "3.5 * 4*B*H*Sq*Sk*D/(2 if causal) (code/Performance_Comparison.py:99-107)"},
+        "frac_of_measured_bf16_peak": value / world / peak["bf16_burst"],
+        "frac_of_measured_sustained_bf16_peak": value / world / peak["bf16_sustained"], "peak_source": peak["source"],
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": None,
+    }
+    if a.impl == "reference":
+        line["impl"] = "reference"; line["config"]["reference"] = ref_note
+        line["gpu_launches"] = None
+
+    def also_workload(name, steps=20, warmup=5):
+        """Another BASELINE config through the same autograd entry, on every rank (its own inputs), L2 flushed between steps."""
+        b2, h2, s2, d2, c2 = WORKLOADS[name]
+        q2, k2, v2, do2 = make_inputs(b2, h2, s2, d2, dtype, 7 + rank, dev)
+        q2.requires_grad_(True); k2.requires_grad_(True); v2.requires_grad_(True)
+        st2 = autograd_step(q2, k2, v2, do2, c2)
+        fwd_only = lambda: attn(q2, k2, v2, c2)
+        for _ in range(10):
+            st2()
+        barrier()
+        t_all = max_over_ranks(sum(x := time_steps(st2, steps, warmup, flush)) / len(x))
+        barrier()
+        t_fwd = max_over_ranks(sum(x := time_steps(fwd_only, steps, warmup, flush)) / len(x))
+        # host time per step: back-to-back enqueue of 100 steps (the launch queue never fills), wall clock until the last call returns
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(100):
+            st2()
+        host_us = (time.perf_counter() - t0) / 100 * 1e6
+        torch.cuda.synchronize()
+        host_us = max_over_ranks(host_us)
+        f2 = 4.0 * b2 * h2 * s2 * s2 * d2 / (2 if c2 else 1)
+        out = dict(workload=f"{name}: B={b2} H={h2} N={s2} D={d2} {'causal' if c2 else 'non-causal'}, the same shape on every rank",
+                   ms_per_step=t_all, ms_fwd=t_fwd, fwd_bwd_tflops=world * 3.5 * f2 / (t_all * 1e-3) / 1e12,
+                   fwd_tflops=world * f2 / (t_fwd * 1e-3) / 1e12,
+                   fwd_bwd_frac_of_measured_peak=3.5 * f2 / (t_all * 1e-3) / 1e12 / peak["bf16_burst"],
+                   fwd_frac_of_measured_peak=f2 / (t_fwd * 1e-3) / 1e12 / peak["bf16_burst"],
+                   host_us_per_step=host_us,
+                   note="through the autograd entry, CUDA events per step, L2 flushed between steps, max over ranks; host_us_per_step = "
+                        "wall time per step() call while enqueueing 100 steps back to back (Python + autograd + launches, no sync)")
+        del q2, k2, v2, do2
+        return out
+
     if not a.no_extras:
-        hin = [x.detach().cpu().pin_memory() for x in (Q, K, V, dO)]
-        hout = [torch.empty_like(h).pin_memory() for h in hin]
+        # ------------------------------- e2e: pinned host buffers in and out -------------------------------
+        hin = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x.detach()) for x in (Q, K, V, dO)]
+        hout = [torch.empty(h.shape, dtype=h.dtype, pin_memory=True) for h in hin]
         if a.impl == "ours":
             # the product's host-buffer entry point: (b,h)-chunked H2D || kernels || D2H on three streams
             from flashattn_b200.host_pipeline import HostAttentionPipeline
-            pipe = HostAttentionPipeline(B, H, S, S, D, dtype, causal, dev, chunks=int(os.environ.get('FA_E2E_CHUNKS', '4')),
+            pipe = HostAttentionPipeline(B, H, S, S, D, dtype, causal, dev, chunks=int(os.environ.get('FA_E2E_CHUNKS', '8' if strong else '4')),
                                          buffers=int(os.environ.get('FA_E2E_BUFFERS', '2')))
             e2e_note = ("flashattn_b200.host_pipeline.HostAttentionPipeline: Q,K,V,dO from pinned host memory, O,dQ,dK,dV back to "
                         "pinned host memory every step; (b,h) chunks, H2D / kernels / D2H overlapped on 3 streams")
@@ -331,68 +428,97 @@ def main():
                 q.grad = None; k.grad = None; v.grad = None
                 dQ_.requires_grad_(False); dK_.requires_grad_(False); dV_.requires_grad_(False)
         barrier()
-        te = time_steps(e2e_step, max(3, a.steps // 3), 3, flush)
+        te = time_steps(e2e_step, max(3, a.steps // 6), 2, None)
         barrier()
-        e_ms = sum(te) / len(te)
-        if dist_on:
-            t = torch.tensor([e_ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e_ms = t.item()
+        e_ms = max_over_ranks(sum(te) / len(te))
         nbytes = sum(h.numel() * h.element_size() for h in hin)
-        e2e = dict(value=world * flops_step / (e_ms * 1e-3) / 1e12, unit="TFLOPS", ms_per_step=e_ms,
-                   h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes,
-                   note=e2e_note)
+        line["e2e"] = dict(value=world * flops_rank / (e_ms * 1e-3) / 1e12, unit="TFLOPS", ms_per_step=e_ms,
+                           h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, note=e2e_note)
+        del hin, hout
+        if a.impl == "ours":
+            del pipe
+        else:
+            del dQ_, dK_, dV_, ddO
 
-    line = {
-        "metric": "fwd_bwd_tflops", "value": value, "unit": "TFLOPS", "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": dtype_name, "data": "synthetic",
-        "config": {"workload": f"{a.workload}: B={B} H={H} N={S} D={D} {'causal' if causal else 'non-causal'} fwd+bwd per GPU",
-                   "global_batch": B * world, "seq_len": S, "parallelism": f"batch x head sharding x{world}, no collective",
-                   "timing": "CUDA events per step on the launch stream through the autograd entry; L2 flushed (256 MiB write) between steps; "
-                             "~1 s of untimed pre-warm steps (clock ramp on a fresh box) before the W warm-up steps",
-                   "flop_model": "3.5 * 4*B*H*Sq*Sk*D/(2 if causal) (code/Performance_Comparison.py:99-107)"},
-        "frac_of_measured_bf16_peak": value / world / peak["bf16_burst"], "peak_source": peak["source"],
-        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-    }
-    if a.impl == "reference":
-        line["impl"] = "reference"; line["config"]["reference"] = ref_note
-        line["gpu_launches"] = None
+        # ------------------------------- also: C2 and C3 through autograd, every rank -------------------------------
+        line["also"] = {wl: also_workload(wl) for wl in ("C2", "C3") if wl != a.workload}
+
+    # ------------------------------- ring: C5 over N >= 2 GPUs -------------------------------
+    if dist_on and a.impl == "ours" and not a.no_extras and not a.no_ring:
+        try:
+            line["ring"] = ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks)
+        except Exception as e:      # the headline line must survive a ring failure; the failure itself is reported
+            line["ring"] = {"error": repr(e)[:400]}
 
     if rank == 0 and not a.no_extras:
         if a.impl == "ours":
-            kb = kernel_breakdown(fa, Q.detach(), K.detach(), V.detach(), dO, causal, max(5, a.steps // 2), 3, flush, peak)
-            dom = max((k for k in kb if kb[k]["bound"] == "tensor" and not k.startswith("two_kernel")), key=lambda k: kb[k]["ms"])
-            gemm = 2.0 * B * H * S * S * D / (2 if causal else 1)
+            kb = kernel_breakdown(fa, Q.detach(), K.detach(), V.detach(), dO, causal, max(5, a.steps // 2), 3, main_flush, peak)
             line["kernels"] = kb
-            line["roofline"] = {"kernel": {"fwd": "fa_fwd_kernel", "dQ": "fa_bwd_dq_kernel", "dKV": "fa_bwd_dkv_kernel",
-                                           "fused": "fa_bwd_fused_kernel"}[dom],
-                                "bound": "tensor", "achieved": kb[dom]["achieved"], "peak": peak["bf16_burst"],
-                                "unit": "TFLOP/s", "frac": kb[dom]["frac"], "traffic": ncu_traffic(a.workload, dom),
-                                "peak_kind": "burst, " + peak["source"],
-                                "algorithmic_flops_per_launch": {"fwd": 2, "dQ": 3, "dKV": 4, "fused": 5}[dom] * gemm}
-            also = {}
-            for wl in ("C3", "C4s"):
-                if wl == a.workload:
-                    continue
-                b2, h2, s2, d2, c2 = WORKLOADS[wl]
-                q2, k2, v2, do2 = make_inputs(b2, h2, s2, d2, dtype, 7, dev)
-                kb2 = kernel_breakdown(fa, q2, k2, v2, do2, c2, 5, 3, flush, peak)
-                f2 = 4.0 * b2 * h2 * s2 * s2 * d2 / (2 if c2 else 1)
-                t_all = sum(kb2[k]["ms"] for k in kb2 if not k.startswith("two_kernel"))
-                also[wl] = dict(fwd_tflops=f2 / (kb2["fwd"]["ms"] * 1e-3) / 1e12,
-                                fwd_frac_of_measured_peak=f2 / (kb2["fwd"]["ms"] * 1e-3) / 1e12 / peak["bf16_burst"],
-                                fwd_bwd_tflops=3.5 * f2 / (t_all * 1e-3) / 1e12,
-                                fwd_bwd_frac_of_measured_peak=3.5 * f2 / (t_all * 1e-3) / 1e12 / peak["bf16_burst"],
-                                ms={k: kb2[k]["ms"] for k in kb2}, note="kernel-only (C-ABI launches, CUDA events), bf16")
-                del q2, k2, v2, do2
-            line["also"] = also
-    if rank == 0 and not a.no_extras:
-        cb = cpu_baseline(B, H, S, D, causal)
+            bw = kb["backward"]
+            wl_key = f"C4_B{B}" if strong else a.workload
+            line["roofline"] = {"kernel": "backward = " + " + ".join({"delta": "fa_delta_kernel", "dQ": "fa_bwd_dq_kernel", "dKV": "fa_bwd_dkv_kernel",
+                                                                     "fused": "fa_bwd_fused_kernel", "convert": "fa_dq_convert_kernel"}[k] for k in bw["kernels"]),
+                                "bound": "tensor", "achieved": bw["achieved"], "peak": peak["bf16_burst"], "unit": "TFLOP/s",
+                                "frac": bw["frac"], "frac_of_sustained_peak": bw["frac_of_sustained_peak"],
+                                "traffic": ncu_traffic(wl_key, "backward"),
+                                "peak_kind": "burst (each kernel timed alone with CUDA events), " + peak["source"],
+                                "algorithmic_flops_per_launch": bw["algorithmic_flops"],
+                                "algorithmic": "2.5 x forward FLOPs = 5 GEMM-units of 2*B*H*Sq*Sk*D/(2 if causal) (SURVEY §8d), over the summed duration of the backward's kernels",
+                                "mma_utilisation": bw["mma_utilisation"], "executed_gemm_units": bw["executed_gemm_units"],
+                                "forward": {"kernel": "fa_fwd_kernel", "achieved": kb["fwd"]["achieved"], "frac": kb["fwd"]["frac"], "ms": kb["fwd"]["ms"],
+                                            "traffic": ncu_traffic(wl_key, "fwd")}}
+        cb = cpu_baseline(Bg, H, S, D, causal)
         line["cpu_baseline"] = cb
     if rank == 0:
         real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
     if dist_on:
         dist.barrier(); dist.destroy_process_group()
     return 0
+
+
+def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks, steps=3):
+    """BASELINE config C5 (B=1 H=32 N=131072 D=128 bf16 causal) sequence-sharded over the ranks: zigzag ring, K/V blocks and the
+    fp32 dK/dV accumulators over NCCL P2P (flashattn_b200.sharding).  Timed like the headline (CUDA events per step, max over
+    ranks); one extra instrumented step gives the per-hop split."""
+    import torch
+    import flashattn_b200.sharding as sh
+    B, H, N, D = C5
+    S2 = N // world
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    q, k, v, do = (torch.randn(B, H, S2, D, device=dev, generator=g, dtype=torch.float32).to(dtype) for _ in range(4))
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+
+    def step(timeline=None):
+        O = sh.ring_flash_attention(q, k, v, None, None, None, timeline)
+        O.backward(do)
+        q.grad = None; k.grad = None; v.grad = None
+
+    step(); step()                                            # communicator set-up and allocator warm-up
+    barrier()
+    ts = []
+    for _ in range(steps):
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        barrier(); s.record(); step(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ms = max_over_ranks(sum(ts) / len(ts))
+    tl = []
+    barrier(); step(tl); torch.cuda.synchronize()
+    ev = dict(tl)
+    hops = []
+    for ph in ("fwd", "bwd"):
+        for s_ in range(world):
+            a_, b_, c_ = ev[f"{ph}{s_}:start"], ev[f"{ph}{s_}:compute_end"], ev[f"{ph}{s_}:end"]
+            hops.append(dict(hop=f"{ph}{s_}", compute_ms=a_.elapsed_time(b_), wait_and_accumulate_ms=b_.elapsed_time(c_)))
+    flops = 3.5 * 4 * B * H * N * N * D / 2
+    val = flops / (ms * 1e-3) / 1e12
+    return dict(workload=f"C5: B={B} H={H} N={N} D={D} causal fwd+bwd, zigzag sequence ring over {world} GPUs (N/{world} = {S2} rows per rank)",
+                ms_per_step=ms, value=val, unit="TFLOPS", per_gpu_tflops=val / world,
+                per_gpu_frac_of_measured_peak=val / world / peak["bf16_burst"],
+                per_gpu_frac_of_measured_sustained_peak=val / world / peak["bf16_sustained"],
+                hops_rank0=hops,
+                compute_ms_rank0=sum(h["compute_ms"] for h in hops), wait_and_accumulate_ms_rank0=sum(h["wait_and_accumulate_ms"] for h in hops),
+                note="compute = the hop's attention kernels + (O,LSE) merges / dQ adds on the compute stream; wait_and_accumulate = waiting for the "
+                     "next K/V block and the incoming dK/dV accumulators (NCCL P2P, posted before the hop's compute) + the fp32 adds into them")
 
 
 if __name__ == "__main__":

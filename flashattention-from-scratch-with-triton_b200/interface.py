@@ -113,19 +113,21 @@ class Ranges:
     @staticmethod
     def from_cu_seqlens(cu_seqlens, total=None, device=None):
         """Packed self-attention (Phase_6.md:160-174): tokens [cu[s], cu[s+1]) form sequence s and attend only inside it.
-        A packed buffer longer than cu[-1] (a padded tail) is handled by treating the pad tokens [cu[-1], total) as one more
-        sequence: the row side and the key side then describe the SAME mask, no real token ever sees a pad token, and the
-        pad rows' outputs / gradients depend on pad data only."""
+        The ranges cover the cu[-1] packed tokens.  A packed BUFFER longer than that (total > cu[-1], a padded tail) is recorded
+        in ``n_tokens`` / ``n_buffer``: flash_attention_varlen then hands the kernels views of the first cu[-1] tokens only, so the
+        tail is never read (tensor-map out-of-bounds rows read as zero — it may hold anything, NaN included) and its outputs and
+        gradients are zero.  Clamping tail tokens into the last sequence instead would make the row side and the key side of the
+        mask disagree (the key side is what the dK/dV and fused kernels use)."""
         cu = torch.as_tensor(cu_seqlens, dtype=torch.int64, device=device)
         last = int(cu[-1])
         total = last if total is None else int(total)
         assert total >= last, f"packed buffer of {total} tokens is shorter than cu_seqlens[-1] = {last}"
-        if total > last:
-            cu = torch.cat([cu, torch.tensor([total], dtype=torch.int64, device=cu.device)])
-        pos = torch.arange(total, device=cu.device)
+        pos = torch.arange(last, device=cu.device)
         sid = torch.searchsorted(cu[1:].contiguous(), pos, right=True).clamp_(max=cu.numel() - 2)
         lo, hi = cu[sid][None], cu[sid + 1][None]
-        return Ranges(lo, hi, lo, hi)
+        r = Ranges(lo, hi, lo, hi)
+        r.n_tokens, r.n_buffer = last, total
+        return r
 
     def validate(self, is_causal=False):
         """Check the documented preconditions (include/fa_sm100.h): all four arrays non-decreasing along the sequence,
@@ -357,9 +359,14 @@ def flash_attention_varlen(q, k, v, cu_seqlens, is_causal=False, *, sm_scale=Non
     total = q.shape[0]
     if ranges is None:
         ranges = Ranges.from_cu_seqlens(cu_seqlens, total, device=q.device)
-    O = flash_attention(q.transpose(0, 1)[None], k.transpose(0, 1)[None], v.transpose(0, 1)[None], is_causal,
+    n = getattr(ranges, "n_tokens", total)                 # tokens the ranges describe; a longer buffer has a padded tail
+    assert ranges.row_lo.shape[1] == n <= total, "ranges do not match the packed buffer"
+    O = flash_attention(q[:n].transpose(0, 1)[None], k[:n].transpose(0, 1)[None], v[:n].transpose(0, 1)[None], is_causal,
                         sm_scale=sm_scale, ranges=ranges)
-    return O[0].transpose(0, 1)
+    O = O[0].transpose(0, 1)
+    if n < total:                                          # pad rows: zeros (and zero gradients, through the view's autograd)
+        O = torch.cat([O, O.new_zeros((total - n,) + tuple(O.shape[1:]))])
+    return O
 
 
 attention = flash_attention

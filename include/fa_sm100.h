@@ -77,7 +77,8 @@ int fa_sm100_bwd_strided(const void* q, const void* k, const void* v, const void
  * [row_lo[b*Sq+i], row_hi[b*Sq+i]) — intersected with keys <= i when `causal` — and the same mask seen from the key side is
  * col_lo/col_hi [B,Sk]: key row j is seen by queries [col_lo[b*Sk+j], col_hi[b*Sk+j]).  All four are device int32 arrays,
  * non-decreasing along the sequence (the kernels derive their tile ranges from the first and last row of a tile), and must
- * describe the same mask; every query row must see at least one key.  Tiles outside the ranges are skipped, not masked:
+ * describe the same mask (interface.Ranges.validate() checks all of this).  A query row may see no key at all: its O is 0, its
+ * LSE -inf and its dQ 0.  Tiles outside the ranges are skipped, not masked:
  * packing N sequences costs the sum of their squares.  Packed [total,H,D] tensors are passed as B = 1, Sq = Sk = total with
  * strides {0, D, H*D}.  NULL ranges = the plain operator. */
 int fa_sm100_fwd_ranges(const void* q, const void* k, const void* v, void* o, float* lse,
@@ -104,7 +105,10 @@ int fa_sm100_bwd_parts(const void* q, const void* k, const void* v, const void* 
  * "next step" (Phase_6.md:54-114).  Each attention probability is kept with probability 1 - p and scaled by 1 / (1 - p); p is
  * quantised to thresh / 256 (one random byte per element).  The keep mask is a pure function of (dropout_seed, batch * H + head,
  * query row, key column) — mix32 / dropout_word in csrc/fa_ptx.cuh; the tests pin it with a numpy restatement — so the backward
- * regenerates it from the same seed; LSE is that of the undropped softmax. */
+ * regenerates it from the same seed; LSE is that of the undropped softmax.
+ * The generator is a counter-based integer hash (two rounds of the "lowbias32" finaliser), NOT Philox: SURVEY §8f-4 names Philox
+ * after the tutorial's sketch (Phase_6.md:54-114), which the reference never implemented, so there is no reference stream to
+ * reproduce; the contract here is "same (seed, coordinates) -> same bit in the forward and in every backward kernel". */
 typedef struct fa_sm100_options {
     const int* row_lo; const int* row_hi;       /* [B,Sq] or NULL */
     const int* col_lo; const int* col_hi;       /* [B,Sk] or NULL (backward only) */

@@ -35,6 +35,26 @@ def _close(a, b, atol=ATOL, rtol=RTOL):
     return torch.allclose(a.float(), b.float(), atol=atol, rtol=rtol)
 
 
+def _norm_err(x, r, atol=ATOL, rtol=RTOL):
+    """max |x - r| / (atol + rtol |r|): the contract holds iff this is <= 1 (code/_verify_func.py:29-31 uses the same quantity)."""
+    r = r.float().to(x.device)
+    return ((x.float() - r).abs() / (atol + rtol * r.abs())).max().item()
+
+
+def _report(test, **kv):
+    """Measured errors of the full-size / reference-comparison tests, appended to gpurun_out/parity_errors.jsonl (if writable)
+    so that a GPU run leaves numbers behind, not just a verdict."""
+    import json
+    try:
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_errors.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=test, **kv)) + "\n")
+    except OSError:
+        pass
+    print(test, kv)
+
+
 SMALL = [
     # B, H, Sq, Sk, D
     (1, 2, 128, 128, 64), (1, 2, 256, 256, 128), (2, 2, 384, 384, 64), (1, 3, 512, 512, 128),
@@ -71,12 +91,15 @@ def test_against_reference_kernel_goldens(path):
     Q, K, V, dO = orc.make_inputs(m["B"], m["H"], m["Sq"], m["Sk"], m["D"], dt, m["seed"])
     O, LSE, dQ, dK, dV = _run_cuda(Q, K, V, dO, bool(m["causal"]))
     assert (LSE - g["LSE"]).abs().max() < LSE_TOL
-    # reference's own verdict rule (rtol=1e-2, atol=1e-3, cos>0.999) between the two fp16 kernels
+    # reference's own verdict rule (rtol=1e-2, atol=1e-3, cos>0.999) between the two 16-bit kernels; fp16 fixtures = the unmodified
+    # kernels (CPU interpreter), bf16 fixtures = the bf16-patched kernels captured on a B200 (make_golden_gpu.py): 8x coarser ulp
+    bound = 4e-3 if dt == torch.float16 else 3.2e-2
     for name, x in (("O", O), ("dQ", dQ), ("dK", dK), ("dV", dV)):
         r = fa.verify_results(g[name], x, name)
-        assert r["cosine_sim"] > 0.9999 and r["max_abs_err"] < 4e-3, (name, r)
-    delta = fa.flash_attention_delta(O.cuda(), dO.cuda()).cpu()
-    assert (delta - g["delta"]).abs().max() < 5e-3
+        assert r["cosine_sim"] > 0.9999 and r["max_abs_err"] < bound, (name, r)
+    if "delta" in g:
+        delta = fa.flash_attention_delta(O.cuda(), dO.cuda()).cpu()
+        assert (delta - g["delta"]).abs().max() < 5e-3
 
 
 def test_c1_config_vs_cpu_sdpa():
@@ -85,30 +108,48 @@ def test_c1_config_vs_cpu_sdpa():
     Qm, Km, Vm, dOm = (torch.randn(1, 4, 512, 64, generator=g) for _ in range(4))
     sO, sdQ, sdK, sdV = orc.sdpa_fp32(Qm, Km, Vm, dOm, False)                 # fp32 master tensors
     for dt in (torch.float16, torch.bfloat16):
-        O, LSE, dQ, dK, dV = _run_cuda(Qm.to(dt), Km.to(dt), Vm.to(dt), dOm.to(dt), False)
-        tol = 1e-2 if dt == torch.float16 else 2e-2     # includes the 16-bit rounding of the INPUTS themselves
-        for x, r in ((O, sO), (dQ, sdQ), (dK, sdK), (dV, sdV)):
-            assert _close(x, r, tol, tol)
-        assert (LSE - orc.lse_bench(Qm.to(dt), Km.to(dt), False)).abs().max() < LSE_TOL
+        Qd, Kd, Vd, dOd = Qm.to(dt), Km.to(dt), Vm.to(dt), dOm.to(dt)
+        O, LSE, dQ, dK, dV = _run_cuda(Qd, Kd, Vd, dOd, False)
+        # the contract (north star): within atol = rtol = 1e-2 of SDPA on the fp32-UPCAST of the 16-bit inputs the kernel saw
+        uO, udQ, udK, udV = orc.sdpa_fp32(Qd, Kd, Vd, dOd, False)
+        errs = {n: _norm_err(x, r) for n, x, r in (("O", O, uO), ("dQ", dQ, udQ), ("dK", dK, udK), ("dV", dV, udV))}
+        # and against the fp32 MASTER tensors (SURVEY §8 C1 caveat): this adds the 16-bit rounding of the inputs themselves, which
+        # is not the kernel's error — reported, bounded at twice the contract
+        errs_master = {n: _norm_err(x, r) for n, x, r in (("O", O, sO), ("dQ", dQ, sdQ), ("dK", dK, sdK), ("dV", dV, sdV))}
+        _report("C1", dtype=str(dt), norm_err_vs_upcast_inputs=errs, norm_err_vs_fp32_masters=errs_master)
+        assert max(errs.values()) <= 1.0, errs
+        assert max(errs_master.values()) <= 2.0, errs_master
+        assert (LSE - orc.lse_bench(Qd, Kd, False)).abs().max() < LSE_TOL
 
 
-def _gpu_truth(Q, K, V, dO, causal):
-    """fp32 materialised attention on the GPU (TF32 off) for shapes too big for the CPU oracle;
-    itself checked against the CPU oracle in test_gpu_truth_is_the_oracle."""
+def _gpu_truth(Q, K, V, dO, causal, q_chunk=4096):
+    """fp32 attention forward + backward on the GPU with plain matmuls (TF32 off), chunked over query rows so that shapes far
+    too big for the CPU oracle (C4: N = 8192, C5: N = 131072) fit: per (b, h) and q chunk S = q K^T is [q_chunk, S_k] fp32.
+    Itself checked against the CPU oracle in test_gpu_truth_is_the_oracle.  Returns O, LSE, dQ, dK, dV (fp32)."""
     torch.backends.cuda.matmul.allow_tf32 = False
-    D = Q.shape[-1]; scale = 1 / math.sqrt(D)
-    outs = []
-    for b in range(Q.shape[0]):
-        q, k, v, do = Q[b].float(), K[b].float(), V[b].float(), dO[b].float()
-        S = q @ k.transpose(-1, -2) * scale
-        if causal:
-            i = torch.arange(q.shape[1], device=q.device); j = torch.arange(k.shape[1], device=q.device)
-            S.masked_fill_(~(i[:, None] >= j[None, :]), float("-inf"))
-        lse = torch.logsumexp(S, -1); P = torch.exp(S - lse[..., None]); o = P @ v
-        dV = P.transpose(-1, -2) @ do; dP = do @ v.transpose(-1, -2)
-        dS = P * (dP - (do * o).sum(-1, keepdim=True))
-        outs.append((o, lse, dS @ k * scale, dS.transpose(-1, -2) @ q * scale, dV))
-    return [torch.stack(x) for x in zip(*outs)]
+    B, H, Sq, D = Q.shape
+    Sk = K.shape[2]
+    scale = 1 / math.sqrt(D)
+    O = torch.empty(B, H, Sq, D, device=Q.device); LSE = torch.empty(B, H, Sq, device=Q.device)
+    dQ = torch.empty_like(O); dK = torch.zeros(B, H, Sk, D, device=Q.device); dV = torch.zeros_like(dK)
+    for b in range(B):
+        for h in range(H):
+            k, v = K[b, h].float(), V[b, h].float()
+            for r0 in range(0, Sq, q_chunk):
+                r1 = min(r0 + q_chunk, Sq)
+                n = min(r1, Sk) if causal else Sk              # keys any row of the chunk can see
+                q, do = Q[b, h, r0:r1].float(), dO[b, h, r0:r1].float()
+                S = q @ k[:n].T * scale
+                if causal:
+                    i = torch.arange(r0, r1, device=Q.device); j = torch.arange(n, device=Q.device)
+                    S.masked_fill_(~(i[:, None] >= j[None, :]), float("-inf"))
+                lse = torch.logsumexp(S, -1); P = torch.exp(S - lse[:, None]); o = P @ v[:n]
+                dP = do @ v[:n].T
+                dS = P * (dP - (do * o).sum(-1, keepdim=True))
+                O[b, h, r0:r1] = o; LSE[b, h, r0:r1] = lse
+                dQ[b, h, r0:r1] = dS @ k[:n] * scale
+                dK[b, h, :n] += dS.T @ q * scale; dV[b, h, :n] += P.T @ do
+    return O, LSE, dQ, dK, dV
 
 
 def test_gpu_truth_is_the_oracle():
@@ -119,28 +160,33 @@ def test_gpu_truth_is_the_oracle():
         assert (a.cpu() - b.float()).abs().max() < 1e-4
 
 
-@pytest.mark.parametrize("cfg", [(4, 16, 2048, 2048, 64, True), (4, 16, 4096, 4096, 128, False)], ids=["C2", "C3"])
+@pytest.mark.parametrize("cfg", [(4, 16, 2048, 64, True), (4, 16, 4096, 128, False), (2, 32, 8192, 128, True), (1, 1, 131072, 128, True)],
+                         ids=["C2", "C3", "C4_shard", "C5_head"])
 def test_baseline_configs_full_size(cfg):
-    """BASELINE configs 2 and 3 at full size, bf16: every element vs fp32 truth; two (b,h) slices
-    additionally vs the CPU oracle."""
-    B, H, S, _, D, causal = cfg
+    """BASELINE configs at full size, bf16, EVERY element against fp32 truth at the contract's atol = rtol = 1e-2 (the measured
+    max normalised error is recorded): C2, C3, one 8-GPU shard of C4 (B = 16/8), and one head of C5 (N = 131072 — the (b,h)
+    problems are independent, so a head is the whole difficulty of the long-context config).  Two (b,h) slices are additionally
+    checked against the CPU oracle where that finishes in seconds."""
+    B, H, S, D, causal = cfg
     g = torch.Generator(device="cuda").manual_seed(0)
     Q, K, V, dO = (torch.randn(B, H, S, D, device="cuda", generator=g).bfloat16() for _ in range(4))
     q = Q.clone().requires_grad_(True); k = K.clone().requires_grad_(True); v = V.clone().requires_grad_(True)
     O = fa.flash_attention(q, k, v, causal); O.backward(dO)
     _, LSE = fa.flash_attention_forward(Q, K, V, causal)
     tO, tLSE, tdQ, tdK, tdV = _gpu_truth(Q, K, V, dO, causal)
-    assert (LSE - tLSE).abs().max() < LSE_TOL
+    lse_err = (LSE - tLSE).abs().max().item()
+    errs, frac_in = {}, {}
     for name, x, r in (("O", O, tO), ("dQ", q.grad, tdQ), ("dK", k.grad, tdK), ("dV", v.grad, tdV)):
-        d = (x.float() - r).abs()
-        # bf16 contract: atol = rtol = 1e-2; over 1e7+ elements allow the 16-bit rounding tail 1.5e-2
-        assert (d <= 1.5e-2 + 1e-2 * r.abs()).all(), (name, d.max().item())
-        assert (d <= 1e-2 + 1e-2 * r.abs()).float().mean() > 0.99999, name
-        assert torch.nn.functional.cosine_similarity(x.float().flatten(), r.flatten(), dim=0) > 0.9999
-    for (b, h) in ((0, 0), (B - 1, H - 1)):
-        sl = lambda t: t[b:b + 1, h:h + 1].cpu()
-        cO, cLSE = orc.sdpa_cpu_flash(sl(Q).float(), sl(K).float(), sl(V).float(), None, causal)
-        assert _close(sl(O.detach()), cO) and (sl(LSE) - cLSE).abs().max() < LSE_TOL
+        errs[name] = _norm_err(x.detach(), r)
+        assert torch.nn.functional.cosine_similarity(x.detach().float().flatten(), r.flatten(), dim=0) > 0.9999, name
+    _report("full_size", cfg=list(cfg), lse_abs_err=lse_err, max_norm_err=errs)
+    assert lse_err < LSE_TOL
+    assert max(errs.values()) <= 1.0, errs                  # atol = rtol = 1e-2 on every element, no tail allowance
+    if S <= 4096:
+        for (b, h) in ((0, 0), (B - 1, H - 1)):
+            sl = lambda t: t[b:b + 1, h:h + 1].cpu()
+            cO, cLSE = orc.sdpa_cpu_flash(sl(Q).float(), sl(K).float(), sl(V).float(), None, causal)
+            assert _close(sl(O.detach()), cO) and (sl(LSE) - cLSE).abs().max() < LSE_TOL
 
 
 def test_properties_at_full_size():
@@ -180,10 +226,11 @@ def test_backward_is_deterministic_and_grads_flow():
     a = fa.flash_attention_backward(Q, K, V, O, dO, LSE, True)
     b = fa.flash_attention_backward(Q, K, V, O, dO, LSE, True)
     assert all(torch.equal(x, y) for x, y in zip(a, b))           # two-kernel backward has no atomics
-    # linearity of the backward in dO (bf16: up to rounding)
+    # linearity of the backward in dO: scaling dO by 2 is exact in bf16 and delta = rowsum(dO o O) doubles exactly, so every
+    # intermediate doubles exactly — the gradients must double BITWISE
     c = fa.flash_attention_backward(Q, K, V, O, (2 * dO.float()).bfloat16(), LSE, True)
     for x, y in zip(a, c):
-        assert _close(2 * x.float(), y.float(), 2e-2, 2e-2)
+        assert torch.equal((2 * x.float()).bfloat16(), y)
 
 
 def test_sm_scale_and_noncontiguous_inputs():
@@ -199,15 +246,19 @@ def test_sm_scale_and_noncontiguous_inputs():
 
 
 def test_error_no_worse_than_reference_triton():
-    """Same inputs through the reference Triton kernels (baseline/_ref) and through this library;
-    error against fp32 truth must not exceed the reference's (25 % slack for rounding noise)."""
+    """Same inputs through the reference Triton kernels (baseline/_ref: fp16 as shipped, bf16 with its dot-operand casts
+    retargeted) and through this library; error against fp32 truth.  North star: "error no worse than the reference Triton
+    kernel's".  Both implementations round P and dS to 16 bits at the same places, so their error distributions are the same
+    and WHICH of the two has the larger maximum over 1e6 elements is a coin flip per tensor; the assertion is therefore
+      max normalised error: ours <= 1.10 * reference + 0.01    and    rms error: ours <= 1.05 * reference,
+    per tensor, with both numbers recorded (gpurun_out/parity_errors.jsonl)."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline"))
     import ref_runner
     why = ref_runner.available()
     if why:
         pytest.skip(why)
-    for dt, causal, D in ((torch.float16, True, 64), (torch.bfloat16, True, 64), (torch.bfloat16, False, 128)):
+    for dt, causal, D in ((torch.float16, True, 64), (torch.bfloat16, True, 64), (torch.bfloat16, False, 128), (torch.float16, True, 128)):
         try:
             ref_fn = ref_runner.ref_flash_attention(dt == torch.bfloat16)
         except Exception as e:  # pragma: no cover
@@ -215,14 +266,18 @@ def test_error_no_worse_than_reference_triton():
         g = torch.Generator(device="cuda").manual_seed(5)
         Q, K, V, dO = (torch.randn(2, 4, 1024, D, device="cuda", generator=g).to(dt) for _ in range(4))
         truth = _gpu_truth(Q, K, V, dO, causal)
-        errs = {}
+        mx, rms = {}, {}
         for name, fn in (("ref", ref_fn), ("ours", fa.flash_attention)):
             q = Q.clone().requires_grad_(True); k = K.clone().requires_grad_(True); v = V.clone().requires_grad_(True)
             O = fn(q, k, v, causal); O.backward(dO)
-            errs[name] = [(x.float() - t).abs().mean().item() for x, t in zip((O, q.grad, k.grad, v.grad),
-                                                                              (truth[0], truth[2], truth[3], truth[4]))]
-        for eo, er in zip(errs["ours"], errs["ref"]):
-            assert eo <= 1.25 * er + 1e-6, (dt, causal, D, errs)
+            pairs = list(zip((O.detach(), q.grad, k.grad, v.grad), (truth[0], truth[2], truth[3], truth[4])))
+            mx[name] = [_norm_err(x, t) for x, t in pairs]
+            rms[name] = [(x.float() - t).pow(2).mean().sqrt().item() for x, t in pairs]
+        _report("vs_reference_triton", dtype=str(dt), causal=causal, D=D, tensors=["O", "dQ", "dK", "dV"], max_norm_err=mx, rms_err=rms)
+        assert max(mx["ours"]) <= 1.0, mx                       # the contract itself
+        for i in range(4):
+            assert mx["ours"][i] <= 1.10 * mx["ref"][i] + 0.01, (dt, causal, D, i, mx)
+            assert rms["ours"][i] <= 1.05 * rms["ref"][i] + 1e-7, (dt, causal, D, i, rms)
 
 
 def test_product_path_is_the_cuda_library():
@@ -366,8 +421,10 @@ def test_gqa_mqa_head_sharing(H, Hk, D, causal):
     rO, _, rdQ, rdKe, rdVe = orc.closed_form(Q, Ke, Ve, dO, causal)
     rdK = rdKe.reshape(B, Hk, G, Sk, D).sum(2); rdV = rdVe.reshape(B, Hk, G, Sk, D).sum(2)
     for name, x, r in (("O", O, rO), ("dQ", q.grad, rdQ), ("dK", k.grad, rdK), ("dV", v.grad, rdV)):
-        tol = 1e-2 if name in ("O", "dQ") else 2e-2          # dK/dV: G-fold sums of bf16-rounded products
-        assert _close(x.detach().cpu(), r, tol, tol), (name, (x.detach().cpu().float() - r.float()).abs().max())
+        # dK/dV are sums over the G query heads of a group, each term within the contract: the sum of G independent rounding
+        # errors is held to atol = 1e-2 * sqrt(G) (rtol stays 1e-2); O and dQ to the contract itself
+        atol = 1e-2 if name in ("O", "dQ") else 1e-2 * math.sqrt(G)
+        assert _close(x.detach().cpu(), r, atol, 1e-2), (name, (x.detach().cpu().float() - r.float()).abs().max())
     # bitwise the same as running the expanded problem's forward through the non-GQA path
     Oe = fa.flash_attention(Q.cuda(), Ke.cuda(), Ve.cuda(), causal)
     assert torch.equal(O.detach(), Oe)
@@ -377,7 +434,7 @@ def test_gqa_mqa_head_sharing(H, Hk, D, causal):
     assert torch.equal(k2.grad, k.grad) and torch.equal(v2.grad, v.grad)      # deterministic
 
 
-def _check_ranges(Q, K, V, dO, causal, ranges, tol_kv=1e-2):
+def _check_ranges(Q, K, V, dO, causal, ranges, tol_kv=None):
     """CUDA path with a Ranges mask against the fp64 closed form with the same mask (dense, on the CPU)."""
     q, k, v = (t.cuda().requires_grad_(True) for t in (Q, K, V))
     O = fa.flash_attention(q, k, v, causal, ranges=ranges)
@@ -389,10 +446,12 @@ def _check_ranges(Q, K, V, dO, causal, ranges, tol_kv=1e-2):
     B, Hk, Sk, D = K.shape
     rdK = rdKe.reshape(B, Hk, G, Sk, D).sum(2); rdV = rdVe.reshape(B, Hk, G, Sk, D).sum(2)
     assert (LSE.cpu() - rLSE.float()).abs().max() < LSE_TOL
+    # dK/dV of a K/V head shared by G query heads are G-term sums: atol = 1e-2 * sqrt(G) (see test_gqa_mqa_head_sharing)
+    tol_kv = 1e-2 * math.sqrt(G) if tol_kv is None else tol_kv
     for name, x, r, tol in (("O", O, rO, 1e-2), ("dQ", q.grad, rdQ, 1e-2), ("dK", k.grad, rdK, tol_kv), ("dV", v.grad, rdV, tol_kv)):
         x = x.detach().cpu()
         assert torch.isfinite(x.float()).all(), name
-        assert _close(x, r, tol, tol), (name, (x.float() - r.float()).abs().max().item())
+        assert _close(x, r, tol, 1e-2), (name, (x.float() - r.float()).abs().max().item())
     import flashattn_b200._cabi as cabi
     assert cabi.last_hang() is None
     return O.detach()
@@ -414,7 +473,7 @@ def test_varlen_packed_sequences(D, H, Hk, causal):
     k = torch.randn(total, Hk, D, generator=g).bfloat16(); v = torch.randn(total, Hk, D, generator=g).bfloat16()
     ranges = fa.Ranges.from_cu_seqlens(cu, total, device="cuda")
     to4 = lambda t: t.transpose(0, 1)[None]
-    O = _check_ranges(to4(q), to4(k), to4(v), to4(do), causal, ranges, tol_kv=2e-2 if H != Hk else 1e-2)
+    O = _check_ranges(to4(q), to4(k), to4(v), to4(do), causal, ranges)
     # the packed entry point returns the same thing in the packed layout
     Op = fa.flash_attention_varlen(q.cuda(), k.cuda(), v.cuda(), torch.tensor(cu), causal)
     assert Op.shape == (total, H, D) and torch.equal(Op, O[0].transpose(0, 1))
@@ -479,3 +538,146 @@ def test_dropout_matches_oracle_mask(D, H, Hk, p, causal):
         rr, _ = orc.closed_form(Q[:1], K[:1, :, :Sq], V[:1, :, :Sq], None, causal, row_ranges=(r.row_lo.cpu(), r.row_hi.cpu()),
                                 keep_mask=keep[:1, :, :, :Sq], keep_scale=scale)
         assert _close(Or.cpu(), rr)
+
+
+def test_native_host_path_equals_python_path():
+    """flash_attention() runs the C++ autograd node (csrc/fa_torch.cpp, _fa_torch.so) for the plain operator; the
+    reference-shaped Python class FlashAttentionFunction is the same operator.  Same kernels, same arguments: bitwise equal
+    (head dim 64: in deterministic mode, the fused backward's dQ summation order is scheduling dependent)."""
+    import flashattn_b200.interface as itf
+    import flashattn_b200._cabi as cabi
+    assert itf._HOST_NATIVE and itf._load_native() is not None
+    for D, dt, causal in ((128, torch.bfloat16, True), (64, torch.float16, False), (64, torch.bfloat16, True)):
+        Q, K, V, dO = (t.cuda() for t in orc.make_inputs(2, 4, 384, 384, D, dt, seed=D))
+        prev = fa.set_deterministic(True)
+        try:
+            res = []
+            n0 = cabi.load().fa_sm100_launch_count()
+            for fn in (lambda q, k, v: fa.flash_attention(q, k, v, causal),
+                       lambda q, k, v: fa.FlashAttentionFunction.apply(q, k, v, causal)):
+                q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+                O = fn(q, k, v); O.backward(dO)
+                res.append((O.detach(), q.grad, k.grad, v.grad))
+            assert cabi.load().fa_sm100_launch_count() - n0 == 8      # (fwd, delta, dQ, dK/dV) x 2: both paths launch the library
+        finally:
+            fa.set_deterministic(prev)
+        for a, b in zip(*res):
+            assert torch.equal(a, b)
+    # sm_scale, GQA and a non-contiguous input (falls back to the strided Python path, same result)
+    Q, K, V, dO = (t.cuda() for t in orc.make_inputs(1, 4, 256, 256, 128, torch.bfloat16, seed=3))
+    O1 = fa.flash_attention(Q, K[:, :2].contiguous(), V[:, :2].contiguous(), True, sm_scale=0.1)
+    O2 = fa.FlashAttentionFunction.apply(Q, K[:, :2].contiguous(), V[:, :2].contiguous(), True, 0.1)
+    assert torch.equal(O1, O2)
+    with pytest.raises(AssertionError):                                   # the reference's asserts (:133-136) still fire first
+        fa.flash_attention(Q.float(), K.float(), V.float())
+
+
+def test_cuda_graph_capture_replays_bitwise():
+    """fwd + bwd captured in a CUDA graph and replayed: no host work per step.  Possible because nothing on the path syncs or
+    memsets (the persistent kernels' work counters reset themselves) and outputs come from the capture's private pool.
+    Replays must reproduce the eager results bitwise (D = 128: every tensor; D = 64: O, dK, dV — the fused backward's dQ is
+    summed in scheduling order) and follow in-place changes of the inputs."""
+    for D in (128, 64):
+        Q, K, V, dO = (t.cuda() for t in orc.make_inputs(2, 4, 512, 512, D, torch.bfloat16, seed=11 + D))
+        q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+
+        def eager():
+            O = fa.flash_attention(q, k, v, True)
+            return (O.detach().clone(),) + tuple(x.clone() for x in torch.autograd.grad(O, (q, k, v), dO))
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                     # warm-up off the capture (kernel attributes, allocator)
+            for _ in range(3):
+                eager()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            O = fa.flash_attention(q, k, v, True)
+            gq, gk, gv = torch.autograd.grad(O, (q, k, v), dO)
+        for trial in range(3):
+            if trial == 2:                                # new data in the captured input buffers
+                with torch.no_grad():
+                    q.copy_(torch.roll(Q, 1, 2)); k.mul_(0.5)
+            ref = eager()
+            graph.replay(); torch.cuda.synchronize()
+            assert torch.equal(O.detach(), ref[0]) and torch.equal(gk, ref[2]) and torch.equal(gv, ref[3]), (D, trial)
+            if D == 128:
+                assert torch.equal(gq, ref[1]), trial
+            else:
+                assert _close(gq, ref[1])
+        del graph
+
+
+@pytest.mark.parametrize("D", [64, 128])
+def test_varlen_padded_tail_is_never_read(D):
+    """A packed buffer longer than cu_seqlens[-1]: the kernels get views of the packed tokens only, so whatever the tail holds
+    (NaN here) never reaches a real token's output or gradient, pad outputs / gradients are zero, and the real part is bitwise
+    the unpadded call."""
+    H, cu, total = 2, [0, 200, 333], 448
+    g = torch.Generator().manual_seed(5)
+    q, k, v, do = (torch.randn(total, H, D, generator=g).bfloat16().cuda() for _ in range(4))
+    for t in (q, k, v, do):
+        t[cu[-1]:] = float("nan")
+    r = fa.Ranges.from_cu_seqlens(cu, total, device="cuda").validate()
+    assert r.n_tokens == cu[-1] and r.n_buffer == total
+    q2, k2, v2 = (t.clone().requires_grad_(True) for t in (q, k, v))
+    O = fa.flash_attention_varlen(q2, k2, v2, torch.tensor(cu), False)
+    assert O.shape == q.shape
+    O.backward(torch.nan_to_num(do))
+    q3, k3, v3 = (t[:cu[-1]].clone().requires_grad_(True) for t in (q, k, v))
+    O3 = fa.flash_attention_varlen(q3, k3, v3, torch.tensor(cu), False, ranges=r)
+    O3.backward(do[:cu[-1]])
+    for a, b in ((O, O3), (q2.grad, q3.grad), (k2.grad, k3.grad), (v2.grad, v3.grad)):
+        assert torch.isfinite(a.float()).all()
+        assert torch.equal(a[:cu[-1]].detach(), b.detach()) and (a[cu[-1]:] == 0).all()
+
+
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("n_empty", [128, 256, 300])
+def test_rows_with_empty_key_range(D, n_empty):
+    """Hand-built Ranges in which the first n_empty query rows see NO key (a whole 128-row tile, a whole 256-row forward item,
+    and a ragged count): those rows get O = 0, LSE = -inf and dQ = 0 — defined values, not the contents of torch.empty — and
+    every other row equals attention over the visible part."""
+    B, H, S = 1, 2, 640
+    Q, K, V, dO = (t.cuda() for t in orc.make_inputs(B, H, S, S, D, torch.bfloat16, seed=n_empty + D))
+    i = torch.arange(S)
+    row_lo = torch.zeros(B, S, dtype=torch.int32); row_hi = torch.where(i < n_empty, 0, S).to(torch.int32)[None]
+    col_lo = torch.full((B, S), n_empty, dtype=torch.int32); col_hi = torch.full((B, S), S, dtype=torch.int32)
+    r = fa.Ranges(row_lo.cuda(), row_hi.cuda(), col_lo.cuda(), col_hi.cuda())
+    q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+    O = fa.flash_attention(q, k, v, False, ranges=r); O.backward(dO)
+    _, LSE = fa.flash_attention_forward(Q, K, V, False, ranges=r)
+    assert (O[:, :, :n_empty] == 0).all() and (LSE[:, :, :n_empty] == float("-inf")).all() and (q.grad[:, :, :n_empty] == 0).all()
+    rO, rLSE, rdQ, rdK, rdV = orc.closed_form(Q[:, :, n_empty:].cpu(), K.cpu(), V.cpu(), dO[:, :, n_empty:].cpu(), False)
+    assert (LSE[:, :, n_empty:].cpu() - rLSE.float()).abs().max() < LSE_TOL
+    for name, x, ref in (("O", O[:, :, n_empty:], rO), ("dQ", q.grad[:, :, n_empty:], rdQ), ("dK", k.grad, rdK), ("dV", v.grad, rdV)):
+        assert _close(x.detach().cpu(), ref), name
+    import flashattn_b200._cabi as cabi
+    assert cabi.last_hang() is None
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs in one process")
+def test_second_device_in_the_same_process():
+    """The > 48 KB dynamic shared memory opt-in is a per-device kernel attribute: the first launch on cuda:1 of a process that
+    has already used cuda:0 must work (fwd + both backward structures)."""
+    for dev in ("cuda:0", "cuda:1"):
+        for D in (64, 128):
+            Q, K, V, dO = (t.to(dev) for t in orc.make_inputs(1, 2, 256, 256, D, torch.bfloat16, seed=1))
+            q, k, v = (t.clone().requires_grad_(True) for t in (Q, K, V))
+            O = fa.flash_attention(q, k, v, True); O.backward(dO)
+            rO, _, rdQ, rdK, rdV = orc.closed_form(Q.cpu(), K.cpu(), V.cpu(), dO.cpu(), True)
+            for x, ref in ((O, rO), (q.grad, rdQ), (k.grad, rdK), (v.grad, rdV)):
+                assert _close(x.detach().cpu(), ref), (dev, D)
+
+
+def test_reference_self_check_compare_with_sdpa():
+    """The reference's own parity routine (code/My_FlashAttention_optimized.py:172-212), run against this library through the
+    drop-in module: SDPA flash backend as yardstick, verify_results verdicts."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "flashattention-from-scratch-with-triton_b200",
+                        "My_FlashAttention_optimized.py")
+    spec = importlib.util.spec_from_file_location("My_FlashAttention_optimized_dropin", path)
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    Q, K, V = (torch.randn(4, 8, 256, 64, device="cuda", generator=g, dtype=torch.float16) for _ in range(3))   # the __main__ shape
+    res = mod.compare_with_sdpa(Q, K, V, True, verbose=False)
+    assert [r["name"] for r in res] == ["O", "dQ", "dK", "dV"] and all(r["passed"] for r in res), res

@@ -25,21 +25,26 @@ def test_golden_fixtures_present():
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_oracle_matches_reference_kernels(path):
-    """Blocked restatement == reference Triton kernels (CPU interpreter) to <= 2 fp16 ulp."""
+    """Blocked restatement == reference Triton kernels: fp16 fixtures (unmodified kernels, CPU interpreter, 64x64 blocks) to
+    <= 2.5 fp16 ulp; bf16 fixtures (bf16-patched kernels captured on a B200 with the autotuner's block sizes,
+    tests/golden/make_golden_gpu.py) to <= 3 bf16 ulp."""
     m, g = _load(path)
     dt = getattr(torch, m["dtype"])
     Q, K, V, dO = orc.make_inputs(m["B"], m["H"], m["Sq"], m["Sk"], m["D"], dt, m["seed"])
     causal = bool(m["causal"])
-    O, LSE = orc.forward_blocked(Q, K, V, causal, m["BLOCK_M"], m["BLOCK_N"])
-    dQ, dK, dV, delta = orc.backward_blocked(Q, K, V, O, dO, LSE, causal, m["BLOCK_M"], m["BLOCK_N"])
-    assert (LSE - g["LSE"]).abs().max() < 5e-6
+    bm, bn = m.get("BLOCK_M", 64), m.get("BLOCK_N", 64)
+    O, LSE = orc.forward_blocked(Q, K, V, causal, bm, bn)
+    dQ, dK, dV, delta = orc.backward_blocked(Q, K, V, O, dO, LSE, causal, bm, bn)
+    bf16 = dt == torch.bfloat16
+    assert (LSE - g["LSE"]).abs().max() < (2e-5 if bf16 else 5e-6)
     for name, x in (("O", O), ("dQ", dQ), ("dK", dK), ("dV", dV)):
         ref = g[name]
-        # <= 2.5 fp16 ulp at the value's magnitude, with an absolute floor of 1 ulp at 0.5 for
-        # near-zero sums (fp32 accumulation order differs between numpy and torch matmuls)
-        ulp = torch.clamp(ref.abs() * 2.0 ** -10, min=2.0 ** -11)
-        assert ((x.float() - ref).abs() <= 2.5 * ulp).all(), name
-    assert (delta - g["delta"]).abs().max() < 2e-3
+        # <= 2.5 fp16 ulp (3 bf16 ulp) at the value's magnitude, with an absolute floor of 1 ulp at 0.5 for
+        # near-zero sums (fp32 accumulation order differs between numpy / torch matmuls / the GPU's tile order)
+        ulp = torch.clamp(ref.abs() * 2.0 ** (-7 if bf16 else -10), min=2.0 ** (-8 if bf16 else -11))
+        assert ((x.float() - ref).abs() <= (3.0 if bf16 else 2.5) * ulp).all(), name
+    if "delta" in g:
+        assert (delta - g["delta"]).abs().max() < 2e-3
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
