@@ -48,7 +48,7 @@ template <int D> struct FwdCfg {
     static constexpr int kOffO = kOffKV + kStages * kTileBytes;
     static constexpr int kOffBar = kOffO + 2 * kOStageBytes;
     static constexpr bool kSepP = (D == 64);               // P in its own TMEM columns [384,512)
-    static constexpr int kNumBars = 2 + 2 + 2 * kStages + 2 + 2 + 2 + 2 + 2 + 2 + 2 + 2;
+    static constexpr int kNumBars = 2 + 2 + 2 * kStages + 2 + 2 + 2 + 2 + 2 + 2 + 2 + 2 + 2;
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 64 + 1024;   // +1024: manual alignment slack
 };
 
@@ -78,6 +78,21 @@ static_assert(2 * FwdRegs<64>::kSoftmax + FwdRegs<64>::kOther <= 504 && 2 * FwdR
 // two tiles by one S MMA) -> on only where P has its own region.
 #ifndef FA_FWD_STAGGER
 #define FA_FWD_STAGGER (C::kSepP)
+#endif
+// Three knobs on the softmax critical path (per K/V tile a warpgroup's chain is: S ready -> load -> row max -> exp -> P stored ->
+// P V and the next S on the tensor pipe; at D=128 that chain, not a pipe, sets the period — profiles/r01: tensor 61 %, XU 54 %):
+//  FA_FWD_MAX3      row max with the 3-input FMNMX3 (64 instead of 128 instructions ahead of the first exponential)
+//  FA_FWD_SPLIT_LD  S is fetched in two halves; the max of the first runs under the TMEM load of the second
+//  FA_FWD_SPLIT_P   (P aliases S, D=128) P is published in two halves: the first four K-steps of P V are issued while the
+//                   second half of the exponentials is still being computed
+#ifndef FA_FWD_MAX3
+#define FA_FWD_MAX3 1
+#endif
+#ifndef FA_FWD_SPLIT_LD
+#define FA_FWD_SPLIT_LD 1
+#endif
+#ifndef FA_FWD_SPLIT_P
+#define FA_FWD_SPLIT_P 1
 #endif
 constexpr float kLazyRescaleLog2 = 8.0f;   // rescale O only when the row max grows by > 2^8 in exp2 units
 
@@ -135,7 +150,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     uint64_t* o_empty = o_full + 2;             // [2]  softmax -> MMA (O_t drained from TMEM)
     uint64_t* s_empty = o_empty + 2;            // [2]  softmax -> MMA (S_t is in registers)           (kSepP)
     uint64_t* pv_done = s_empty + 2;            // [2]  MMA -> softmax (P_t V of this iteration done)  (kSepP)
-    uint64_t* sched_full = pv_done + 2;         // [2]
+    uint64_t* p_half = pv_done + 2;             // [2]  softmax -> MMA (first half of P_t in TMEM)        (FA_FWD_SPLIT_P)
+    uint64_t* sched_full = p_half + 2;          // [2]
     uint64_t* sched_empty = sched_full + 2;     // [2]
     volatile int* sched_item = reinterpret_cast<volatile int*>(sched_empty + 2);   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sched_item) + 2);
@@ -148,7 +164,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
             mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 128);
-            mbar_init(&s_empty[i], 128); mbar_init(&pv_done[i], 1);
+            mbar_init(&s_empty[i], 128); mbar_init(&pv_done[i], 1); mbar_init(&p_half[i], 128);
             mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], C::kSepP ? 10 : 9);  // MMA thread(s) + 8 softmax warps
         }
         for (int i = 0; i < C::kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], C::kSepP ? 2 : 1); }   // released by every MMA thread
@@ -323,12 +339,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                             idesc_s, k > 0);
                 }
             };
-            auto issue_pv = [&](int t, uint32_t st, bool acc) {   // O_t (+)= P_t V
+            auto issue_pv_k = [&](int t, uint32_t st, bool acc, int k0, int k1) {   // O_t (+)= P_t V, K-steps [k0, k1)
                 const uint32_t b = skv_addr + st * C::kTileBytes;
                 #pragma unroll
-                for (int k = 0; k < 8; ++k)
+                for (int k = k0; k < k1; ++k)
                     umma_ts_e(tmem + 256 + t * D, tmem + t * 128 + k * 8, make_smem_desc(b + k * 2048, 16384, 1024),
                             idesc_pv, acc || k > 0);
+            };
+            uint32_t ph_h = 0;                           // bit t = parity of p_half[t] to wait for next
+            // P_t(j) V(j): with FA_FWD_SPLIT_P the first four K-steps go out as soon as the first half of P_t is in TMEM
+            auto do_pv = [&](int t, uint32_t st, int j, uint32_t& ph_pp, uint32_t& ph_oo) {
+                const uint32_t bit = 1u << t;
+                if (FA_FWD_SPLIT_P) {
+                    mbar_wait(&p_half[t], (ph_h >> t) & 1, 209 + t); ph_h ^= bit;
+                    if (j == 0) { mbar_wait(&o_empty[t], ((ph_oo >> t) & 1) ^ 1, 205 + 2 * t); ph_oo ^= bit; }
+                    tc_fence_after();
+                    issue_pv_k(t, st, j > 0, 0, 4);
+                    mbar_wait(&p_full[t], (ph_pp >> t) & 1, 204 + 2 * t); ph_pp ^= bit;
+                    tc_fence_after();
+                    issue_pv_k(t, st, true, 4, 8);
+                } else {
+                    mbar_wait(&p_full[t], (ph_pp >> t) & 1, 204 + 2 * t); ph_pp ^= bit;
+                    if (j == 0) { mbar_wait(&o_empty[t], ((ph_oo >> t) & 1) ^ 1, 205 + 2 * t); ph_oo ^= bit; }
+                    tc_fence_after();
+                    issue_pv_k(t, st, j > 0, 0, 8);
+                }
             };
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it & 1;
@@ -363,10 +398,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         const bool more = (j + 1 < n);
                         kv_wait(kv_cnt);                       // V(j)
                         if (j < n0) {
-                            mbar_wait(&p_full[0], ph_p & 1, 204); ph_p ^= 1;
-                            if (j == 0) { mbar_wait(&o_empty[0], (ph_oe & 1) ^ 1, 205); ph_oe ^= 1; }
-                            tc_fence_after();
-                            issue_pv(0, vst, j > 0);
+                            do_pv(0, vst, j, ph_p, ph_oe);
                             if (j == n0 - 1) tc_commit_e(&o_full[0]);
                         }
                         if (more) kv_wait(kv_cnt + 1);         // K(j+1)
@@ -376,10 +408,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                             if (j + 1 == n0 - 1) tc_commit_e(&q_empty[0]);
                         }
                         if (j < n1) {
-                            mbar_wait(&p_full[1], (ph_p >> 1) & 1, 206); ph_p ^= 2;
-                            if (j == 0) { mbar_wait(&o_empty[1], ((ph_oe >> 1) & 1) ^ 1, 207); ph_oe ^= 2; }
-                            tc_fence_after();
-                            issue_pv(1, vst, j > 0);
+                            do_pv(1, vst, j, ph_p, ph_oe);
                             if (j == n1 - 1) tc_commit_e(&o_full[1]);
                         }
                         tc_commit_e(&kv_empty[vst]); ++kv_cnt;
@@ -452,29 +481,43 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 mbar_wait(&s_full[t], ph_s, 301); ph_s ^= 1;
                 tc_fence_after();
                 uint32_t s[4][32];
-                #pragma unroll
-                for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, s[q]);
-                tc_wait_ld();
-                if constexpr (C::kSepP) { tc_fence_before(); mbar_arrive(&s_empty[t]); }   // S_t(j+1) may overwrite S_t now
                 // element mask only on tiles that straddle the diagonal or the end of K
                 const int kbase = (kRanges ? jb + j : j) * 128;
                 int cmax = (kRanges ? k_hi : p.Sk) - 1 - kbase;             // last valid column in this tile
                 if (p.causal) cmax = min(cmax, row_g - kbase);
                 const int cmin = kRanges ? k_lo - kbase : 0;                // first valid column (> 0 only with row ranges)
-                if (cmax < 127 || cmin > 0) {
-                    #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                auto mask_half = [&](int q0) {
+                    if (cmax < 127 || cmin > 0) {
                         #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (q * 32 + i > cmax || q * 32 + i < cmin) s[q][i] = 0xff800000u;  // -inf
-                }
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-                #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    mx0 = fmaxf(mx0, __uint_as_float(s[0][i])); mx1 = fmaxf(mx1, __uint_as_float(s[1][i]));
-                    mx2 = fmaxf(mx2, __uint_as_float(s[2][i])); mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
-                }
-                const float m_new = fmaxf(fmaxf(m, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+                        for (int q = q0; q < q0 + 2; ++q)
+                            #pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (q * 32 + i > cmax || q * 32 + i < cmin) s[q][i] = 0xff800000u;  // -inf
+                    }
+                };
+                auto max_half = [&](int q0, float& a, float& b) {
+                    a = -INFINITY; b = -INFINITY;
+                    if (FA_FWD_MAX3) {
+                        #pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            a = fmax3(a, __uint_as_float(s[q0][i]), __uint_as_float(s[q0][i + 1]));
+                            b = fmax3(b, __uint_as_float(s[q0 + 1][i]), __uint_as_float(s[q0 + 1][i + 1]));
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int i = 0; i < 32; ++i) { a = fmaxf(a, __uint_as_float(s[q0][i])); b = fmaxf(b, __uint_as_float(s[q0 + 1][i])); }
+                    }
+                };
+                float mx0, mx1, mx2, mx3;
+                tmem_ld32(tS, s[0]); tmem_ld32(tS + 32, s[1]);
+                if (FA_FWD_SPLIT_LD) tc_wait_ld();
+                tmem_ld32(tS + 64, s[2]); tmem_ld32(tS + 96, s[3]);
+                if (FA_FWD_SPLIT_LD) { mask_half(0); max_half(0, mx0, mx1); }    // under the TMEM load of the second half
+                tc_wait_ld();
+                if constexpr (C::kSepP) { tc_fence_before(); mbar_arrive(&s_empty[t]); }   // S_t(j+1) may overwrite S_t now
+                if (!FA_FWD_SPLIT_LD) { mask_half(0); max_half(0, mx0, mx1); }
+                mask_half(2); max_half(2, mx2, mx3);
+                const float m_new = FA_FWD_MAX3 ? fmaxf(fmax3(m, mx0, mx1), fmaxf(mx2, mx3)) : fmaxf(fmaxf(m, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
                 if (j == 0) {
                     m = m_new;
                 } else {
@@ -526,6 +569,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                             p1 = dropout_keep(w, kcol + 1, p.drop.thresh) ? p1 * p.drop.scale : 0.f;
                         }
                         pk[i] = pack2<kBf16>(p0, p1);
+                    }
+                    if (FA_FWD_SPLIT_P && !C::kSepP && q == 2) {   // columns 0..63 of P_t were stored a quarter of the exponentials ago:
+                        tc_wait_st(); tc_fence_before();           // release the first four K-steps of P_t V while the rest is computed
+                        mbar_arrive(&p_half[t]);
                     }
                     tmem_st16(tP + q * 16, pk);
                 }

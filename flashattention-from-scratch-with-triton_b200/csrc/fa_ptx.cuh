@@ -30,6 +30,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float ex2_approx_ordered(float x) {
     float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {          // FMNMX3 (sm_100)
+    float y; asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y;
+}
 __device__ __forceinline__ float lg2_approx(float x) {
     float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }

@@ -319,7 +319,7 @@ class ThreadRingComm:
 
         class _P:
             def wait(self_inner):
-                got = comm.queues[comm.rank].get(timeout=120)
+                got = comm.queues[comm.rank].get(timeout=60)
                 for dst, src in zip(recv, got):
                     dst.copy_(src)
         return _P()

@@ -49,11 +49,12 @@ def test_virtual_ring_on_one_gpu(world, D, Hk):
 
     def rank_fn(rank, comm):
         torch.cuda.set_device(0)
+        # ring_attention_forward / _backward called directly: autograd would run every simulated rank's backward on the ONE
+        # autograd worker thread of the device, where they cannot wait for each other
         q, k, v, do = (sh.zigzag_split(t, rank, world).cuda() for t in (Q, K, V, dO))
-        q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
-        O = sh.ring_flash_attention(q, k, v, None, comm, 2)        # two sub-launches per hop
-        O.backward(do)
-        return O.detach().cpu(), q.grad.cpu(), k.grad.cpu(), v.grad.cpu()
+        O, LSE = sh.ring_attention_forward(q, k, v, None, None, comm, 2)        # two sub-launches per hop
+        dq, dk, dv = sh.ring_attention_backward(q, k, v, O, do, LSE, None, None, comm, 2)
+        return O.cpu(), dq.cpu(), dk.cpu(), dv.cpu()
 
     outs = sh.run_virtual_ring(world, rank_fn)
     torch.cuda.synchronize()
@@ -83,10 +84,8 @@ def test_virtual_ring_c5_head_vs_one_shot_and_truth():
     def rank_fn(rank, comm):
         torch.cuda.set_device(0)
         q, k, v, do = (sh.zigzag_split(t, rank, world) for t in (Q, K, V, dO))
-        q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
-        O = sh.ring_flash_attention(q, k, v, None, comm, 1)
-        O.backward(do)
-        return O.detach(), q.grad, k.grad, v.grad
+        O, LSE = sh.ring_attention_forward(q, k, v, None, None, comm, 1)
+        return (O,) + tuple(sh.ring_attention_backward(q, k, v, O, do, LSE, None, None, comm, 1))
 
     outs = sh.run_virtual_ring(world, rank_fn)
     q1, k1, v1 = (t.clone().requires_grad_(True) for t in (Q, K, V))
