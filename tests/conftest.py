@@ -10,23 +10,27 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 with `-m gpu`)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices on one box (run with `gpurun --gpus 2 -- python -m pytest tests -m multigpu`); "
+                                       "kept out of `-m gpu` so the 1-GPU run has nothing to skip")
 
 
-def _has_cuda():
+def _n_cuda():
     try:
         import torch
-        return torch.cuda.is_available()
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
     except Exception:
-        return False
+        return 0
 
 
 def pytest_collection_modifyitems(config, items):
-    if _has_cuda():
-        return
+    n = _n_cuda()
     skip = pytest.mark.skip(reason="no CUDA device in this container")
+    skip2 = pytest.mark.skip(reason="needs >= 2 CUDA devices")
     for it in items:
-        if "gpu" in it.keywords:
+        if "gpu" in it.keywords and n < 1:
             it.add_marker(skip)
+        if "multigpu" in it.keywords and n < 2:
+            it.add_marker(skip2)
 
 
 @pytest.fixture(scope="session")
