@@ -4,6 +4,7 @@
 #include "fa_fwd.cuh"
 #include "fa_bwd.cuh"
 #include "fa_bwd_fused.cuh"
+#include "fa_bwd_fused128.cuh"
 #include "fa_aux.cuh"
 #include "../../include/fa_sm100.h"
 
@@ -368,7 +369,7 @@ int fa_sm100_bwd_opt(const void* q, const void* k, const void* v, const void* o,
 }
 
 size_t fa_sm100_bwd_fused_workspace(int B, int H, int Sq, int D) {
-    if (D != 64 || B <= 0 || H <= 0 || Sq <= 0) return 0;
+    if ((D != 64 && D != 128) || B <= 0 || H <= 0 || Sq <= 0) return 0;
     return (size_t)B * H * Sq * D * sizeof(float);
 }
 
@@ -390,7 +391,8 @@ int fa_sm100_bwd_fused_opt(const void* q, const void* k, const void* v, const vo
     if (parts == 0) parts = FA_BWD_DELTA | FA_BWD_FUSED | FA_BWD_CONVERT;
     if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv || !delta || !dq_acc) return fail(FA_ERR_NULL, "null tensor pointer");
     if (int rc = check_common(B, H, Sq, Sk, D, dtype)) return rc;
-    if (D != 64) return fail(FA_ERR_HEADDIM, "the fused backward exists for head dim 64 only (TMEM budget), got %d", D);
+    if (D == 128 && (col_lo || drop.thresh))
+        return fail(FA_ERR_HEADDIM, "the fused backward at head dim 128 has no range-mask / dropout instantiation: use fa_sm100_bwd_opt");
     if (Hk <= 0 || H % Hk) return fail(FA_ERR_SHAPE, "K/V heads %d must divide query heads %d", Hk, H);
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dout) || !aligned16(dq) ||
         !aligned16(dk) || !aligned16(dv) || !aligned16(lse) || !aligned16(delta) || !aligned16(dq_acc))
@@ -432,8 +434,12 @@ int fa_sm100_bwd_fused_opt(const void* q, const void* k, const void* v, const vo
     p.hc_dkv = heads_per_chunk(BH / p.G, 4.0 * ((double)p.G * Sq + Sk) * D);
     p.sched_dkv = dev->sched_ring + sched_slot(); p.sched_dq = nullptr;
     p.dev = dev->ordinal;
-    rc = dtype ? launch_bwd_fused_t<true>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts)
-               : launch_bwd_fused_t<false>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts);
+    if (D == 128)
+        rc = dtype ? launch_bwd_fused128_t<true>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts)
+                   : launch_bwd_fused128_t<false>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts);
+    else
+        rc = dtype ? launch_bwd_fused_t<true>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts)
+                   : launch_bwd_fused_t<false>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts);
     g_launches += ((parts & FA_BWD_FUSED) ? 1 : 0) + ((parts & FA_BWD_CONVERT) ? 1 : 0);
     return rc == 0 ? 0 : cuda_fail((cudaError_t)rc, "fa_bwd_fused kernels launch");
 }

@@ -92,8 +92,16 @@ static_assert(2 * FwdRegs<64>::kSoftmax + FwdRegs<64>::kOther <= 504 && 2 * FwdR
 #define FA_FWD_SPLIT_LD 1
 #endif
 #ifndef FA_FWD_SPLIT_P
-#define FA_FWD_SPLIT_P 1
+#define FA_FWD_SPLIT_P 0        // measured: no change (profiles/r02_ab_fwd_knobs_negative_result.jsonl); excluded by FA_FWD_SPEC
 #endif
+//  FA_FWD_SPEC      speculative exponentials against the stale row maximum (see the softmax loop): 1 = where P aliases S (D = 128),
+//                   2 = every head dim, 0 = off
+// Measured (profiles/r02_ab_fwd_speculative_max_negative_result.jsonl): correct (102 GPU tests green) but 6-7 % SLOWER at D = 128
+// (C3 fwd 0.443 -> 0.473 ms) and 14-18 % slower at D = 64 — the load + max were not the exposed part of the chain -> off.
+#ifndef FA_FWD_SPEC
+#define FA_FWD_SPEC 0
+#endif
+static_assert(!(FA_FWD_SPEC && FA_FWD_SPLIT_P), "a speculative tile may be redone: P cannot be published in halves");
 constexpr float kLazyRescaleLog2 = 8.0f;   // rescale O only when the row max grows by > 2^8 in exp2 units
 
 // iterations (128-wide K/V tiles) that tile `t` of the item starting at row q0 must visit
@@ -436,6 +444,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         uint8_t* sOt = sO + t * C::kOStageBytes;
         uint32_t ph_s = 0, ph_o = 0, ph_pv = 0;
         const float c2 = p.scale_log2;
+        constexpr bool kSpec = (FA_FWD_SPEC == 2) || (FA_FWD_SPEC == 1 && !C::kSepP);
         if (FA_FWD_STAGGER && t == 1) named_bar_arrive(3, 256);        // warpgroup 0 takes the first turn
         for (uint32_t it = 0;; ++it) {
             const uint32_t slot = it & 1;
@@ -508,75 +517,110 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         for (int i = 0; i < 32; ++i) { a = fmaxf(a, __uint_as_float(s[q0][i])); b = fmaxf(b, __uint_as_float(s[q0 + 1][i])); }
                     }
                 };
+                // exponentials of quarters [q_lo, q_hi) of the tile against the row maximum `mm`: p -> 16-bit -> TMEM, row sum into
+                // the two pair accumulators (fp32 p before rounding, ref :111)
+                const uint64_t c2v = pack_f2(c2, c2);
+                uint64_t lA = pack_f2(0.f, 0.f), lB = lA;
+                auto exp_quarters = [&](int q_lo, int q_hi, float mm) {
+                    const float neg_mc = (mm == -INFINITY) ? 0.f : -mm * c2;
+                    const uint64_t nmv = pack_f2(neg_mc, neg_mc);
+                    #pragma unroll
+                    for (int q = q_lo; q < q_hi; ++q) {
+                        uint32_t pk[16];
+                        #pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const uint64_t xv = ffma2(pack_u2(s[q][2 * i], s[q][2 * i + 1]), c2v, nmv);
+                            float p0, p1;
+                            if ((i % FA_FWD_POLY_DEN) < FA_FWD_POLY_NUM) {
+                                ex2_poly2(xv, p0, p1);
+                            } else {
+                                float x0, x1; unpack_f2(xv, x0, x1);
+                                p0 = ex2_approx(x0); p1 = ex2_approx(x1);
+                            }
+                            if (i & 1) lB = fadd2(lB, pack_f2(p0, p1)); else lA = fadd2(lA, pack_f2(p0, p1));   // l: before dropout
+                            if constexpr (kDropout) {              // O accumulates the dropped-out, rescaled P; LSE / l do not
+                                const uint32_t kcol = (uint32_t)(kbase + q * 32 + 2 * i);
+                                const uint32_t w = dropout_word(drop_key, p.drop.seed1, kcol >> 2);
+                                p0 = dropout_keep(w, kcol, p.drop.thresh) ? p0 * p.drop.scale : 0.f;
+                                p1 = dropout_keep(w, kcol + 1, p.drop.thresh) ? p1 * p.drop.scale : 0.f;
+                            }
+                            pk[i] = pack2<kBf16>(p0, p1);
+                        }
+                        if (FA_FWD_SPLIT_P && !C::kSepP && q == 2) {   // columns 0..63 of P_t were stored a quarter of the exponentials ago:
+                            tc_wait_st(); tc_fence_before();           // release the first four K-steps of P_t V while the rest is computed
+                            mbar_arrive(&p_half[t]);
+                        }
+                        tmem_st16(tP + q * 16, pk);
+                    }
+                };
+                // O_t and l rescaled from row maximum m to m_new (warp-collective TMEM traffic)
+                auto rescale_to = [&](float m_new) {
+                    // m = -inf -> 0.  A row that is STILL fully masked (range masks: its keys start tiles later) is rescaled with
+                    // its warp (the decision is warp-uniform): -inf - -inf would poison l and O with NaN
+                    const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx((m - m_new) * c2);
+                    l *= corr;
+                    #pragma unroll
+                    for (int q = 0; q < D / 32; ++q) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + q * 32, o);
+                        tc_wait_ld();
+                        #pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                        tmem_st32(tO + q * 32, o);
+                    }
+                    m = m_new;
+                };
                 float mx0, mx1, mx2, mx3;
                 tmem_ld32(tS, s[0]); tmem_ld32(tS + 32, s[1]);
-                if (FA_FWD_SPLIT_LD) tc_wait_ld();
+                if (FA_FWD_SPLIT_LD || kSpec) tc_wait_ld();
                 tmem_ld32(tS + 64, s[2]); tmem_ld32(tS + 96, s[3]);
-                if (FA_FWD_SPLIT_LD) { mask_half(0); max_half(0, mx0, mx1); }    // under the TMEM load of the second half
-                tc_wait_ld();
-                if constexpr (C::kSepP) { tc_fence_before(); mbar_arrive(&s_empty[t]); }   // S_t(j+1) may overwrite S_t now
-                if (!FA_FWD_SPLIT_LD) { mask_half(0); max_half(0, mx0, mx1); }
-                mask_half(2); max_half(2, mx2, mx3);
-                const float m_new = FA_FWD_MAX3 ? fmaxf(fmax3(m, mx0, mx1), fmaxf(mx2, mx3)) : fmaxf(fmaxf(m, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
-                if (j == 0) {
-                    m = m_new;
-                } else {
-                    if constexpr (C::kSepP) {      // P_t(j-1) V(j-1) must be complete before O_t or P_t is touched
-                        mbar_wait(&pv_done[t], ph_pv, 303); ph_pv ^= 1; tc_fence_after();
-                    }
-                    // lazy rescale (warp-uniform decision: tcgen05.ld/st are warp-collective)
-                    const bool need = (m_new - m) * c2 > kLazyRescaleLog2;
+                if (kSpec && j > 0) {
+                    // Speculative tile (every tile but the first): the exponentials start against the STALE row maximum as soon as the
+                    // first half of S_t is in registers — the TMEM load of the second half and the whole max reduction leave the
+                    // S -> P critical path (it, not a pipe, sets the period at D = 128: the softmax warps spend 37 % of their time
+                    // waiting for S_t, profiles/r02).  The tile's true maximum is reduced alongside; if it exceeds the stale one by
+                    // more than the lazy-rescale threshold (rare after the first tiles), O_t / l are rescaled and the tile is redone
+                    // with the new maximum, so P never exceeds 2^threshold (fp16-safe) — the same bound as before.
+                    if constexpr (C::kSepP) { mbar_wait(&pv_done[t], ph_pv, 303); ph_pv ^= 1; tc_fence_after(); }
+                    mask_half(0);
+                    if (FA_FWD_STAGGER) named_bar_sync(3 + t, 256);
+                    exp_quarters(0, 2, m);
+                    max_half(0, mx0, mx1);
+                    tc_wait_ld();
+                    if constexpr (C::kSepP) { tc_fence_before(); mbar_arrive(&s_empty[t]); }
+                    mask_half(2);
+                    exp_quarters(2, 4, m);
+                    max_half(2, mx2, mx3);
+                    const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                    const bool need = (m_tile - m) * c2 > kLazyRescaleLog2 || (m == -INFINITY && m_tile != -INFINITY);
                     if (__any_sync(0xffffffffu, need)) {
-                        // m = -inf -> 0.  A row that is STILL fully masked (range masks: its keys start tiles later) is rescaled with
-                        // its warp (the decision is warp-uniform): -inf - -inf would poison l and O with NaN
-                        const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx((m - m_new) * c2);
-                        l *= corr;
-                        #pragma unroll
-                        for (int q = 0; q < D / 32; ++q) {
-                            uint32_t o[32];
-                            tmem_ld32(tO + q * 32, o);
-                            tc_wait_ld();
-                            #pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-                            tmem_st32(tO + q * 32, o);
-                        }
+                        tc_wait_st();                              // the speculative P stores are ordered before the redo's
+                        rescale_to(fmaxf(m, m_tile));
+                        lA = pack_f2(0.f, 0.f); lB = lA;
+                        exp_quarters(0, 4, m);
+                    }
+                    if (FA_FWD_STAGGER) named_bar_arrive(4 - t, 256);
+                } else {
+                    if (FA_FWD_SPLIT_LD && !kSpec) { mask_half(0); max_half(0, mx0, mx1); }    // under the TMEM load of the second half
+                    tc_wait_ld();
+                    if constexpr (C::kSepP) { tc_fence_before(); mbar_arrive(&s_empty[t]); }   // S_t(j+1) may overwrite S_t now
+                    if (!FA_FWD_SPLIT_LD || kSpec) { mask_half(0); max_half(0, mx0, mx1); }
+                    mask_half(2); max_half(2, mx2, mx3);
+                    const float m_new = FA_FWD_MAX3 ? fmaxf(fmax3(m, mx0, mx1), fmaxf(mx2, mx3)) : fmaxf(fmaxf(m, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+                    if (j == 0) {
                         m = m_new;
-                    }
-                }
-                const float neg_mc = (m == -INFINITY) ? 0.f : -m * c2;
-                if (FA_FWD_STAGGER) named_bar_sync(3 + t, 256);              // my turn on the exp unit
-                // p = exp2(s*c - m*c): FFMA2 on pairs, two pair-accumulators for the row sum (fp32, before rounding: ref :111)
-                const uint64_t c2v = pack_f2(c2, c2), nmv = pack_f2(neg_mc, neg_mc);
-                uint64_t lA = pack_f2(0.f, 0.f), lB = lA;
-                #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t pk[16];
-                    #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint64_t xv = ffma2(pack_u2(s[q][2 * i], s[q][2 * i + 1]), c2v, nmv);
-                        float p0, p1;
-                        if ((i % FA_FWD_POLY_DEN) < FA_FWD_POLY_NUM) {
-                            ex2_poly2(xv, p0, p1);
-                        } else {
-                            float x0, x1; unpack_f2(xv, x0, x1);
-                            p0 = ex2_approx(x0); p1 = ex2_approx(x1);
+                    } else {
+                        if constexpr (C::kSepP) {      // P_t(j-1) V(j-1) must be complete before O_t or P_t is touched
+                            mbar_wait(&pv_done[t], ph_pv, 303); ph_pv ^= 1; tc_fence_after();
                         }
-                        if (i & 1) lB = fadd2(lB, pack_f2(p0, p1)); else lA = fadd2(lA, pack_f2(p0, p1));   // l: before dropout
-                        if constexpr (kDropout) {              // O accumulates the dropped-out, rescaled P; LSE / l do not
-                            const uint32_t kcol = (uint32_t)(kbase + q * 32 + 2 * i);
-                            const uint32_t w = dropout_word(drop_key, p.drop.seed1, kcol >> 2);
-                            p0 = dropout_keep(w, kcol, p.drop.thresh) ? p0 * p.drop.scale : 0.f;
-                            p1 = dropout_keep(w, kcol + 1, p.drop.thresh) ? p1 * p.drop.scale : 0.f;
-                        }
-                        pk[i] = pack2<kBf16>(p0, p1);
+                        // lazy rescale (warp-uniform decision: tcgen05.ld/st are warp-collective)
+                        const bool need = (m_new - m) * c2 > kLazyRescaleLog2;
+                        if (__any_sync(0xffffffffu, need)) rescale_to(m_new);
                     }
-                    if (FA_FWD_SPLIT_P && !C::kSepP && q == 2) {   // columns 0..63 of P_t were stored a quarter of the exponentials ago:
-                        tc_wait_st(); tc_fence_before();           // release the first four K-steps of P_t V while the rest is computed
-                        mbar_arrive(&p_half[t]);
-                    }
-                    tmem_st16(tP + q * 16, pk);
+                    if (FA_FWD_STAGGER) named_bar_sync(3 + t, 256);              // my turn on the exp unit
+                    exp_quarters(0, 4, m);
+                    if (FA_FWD_STAGGER) named_bar_arrive(4 - t, 256);            // hand the turn to the other warpgroup
                 }
-                if (FA_FWD_STAGGER) named_bar_arrive(4 - t, 256);            // hand the turn to the other warpgroup
                 {
                     float a0, a1; unpack_f2(fadd2(lA, lB), a0, a1);
                     l += a0 + a1;

@@ -23,6 +23,7 @@ using torch::autograd::AutogradContext;
 using torch::autograd::variable_list;
 
 bool g_deterministic = false;
+bool g_fused128 = false;      // head dim 128: fused single-pass backward (csrc/fa_bwd_fused128.cuh) instead of dQ + dK/dV
 
 inline int dtype_code(const Tensor& t) { return t.scalar_type() == at::kBFloat16 ? FA_DTYPE_BF16 : FA_DTYPE_FP16; }
 
@@ -55,7 +56,7 @@ std::tuple<Tensor, Tensor, Tensor> backward_impl(const Tensor& Q, const Tensor& 
     Tensor dQ = at::empty_like(Q), dK = at::empty_like(K), dV = at::empty_like(V);  // reference :71-73
     Tensor delta = at::empty({B, H, Sq}, Q.options().dtype(at::kFloat));
     auto st = c10::cuda::getCurrentCUDAStream(Q.device().index());
-    if (D == 64 && !g_deterministic) {
+    if ((D == 64 || (D == 128 && g_fused128)) && !g_deterministic) {
         // fused single-pass backward (delta + zeroing, fused dK/dV/dQ, dQ conversion); fp32 dQ workspace
         Tensor acc = at::empty({B, H, Sq, D}, Q.options().dtype(at::kFloat));
         const int rc = fa_sm100_bwd_fused(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
@@ -113,4 +114,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("backward", &backward_impl, "(dQ, dK, dV) = backward(Q, K, V, O, dO, LSE, causal, sm_scale)");
     m.def("set_deterministic", [](bool f) { const bool p = g_deterministic; g_deterministic = f; return p; });
     m.def("is_deterministic", [] { return g_deterministic; });
+    m.def("set_fused128", [](bool f) { const bool p = g_fused128; g_fused128 = f; return p; });
 }

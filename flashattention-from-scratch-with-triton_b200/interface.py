@@ -50,6 +50,7 @@ def _load_native():
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         mod.set_deterministic(_deterministic)
+        mod.set_fused128(globals().get("_fused128", False))
         _native = mod
     return _native
 
@@ -256,8 +257,22 @@ def is_deterministic() -> bool:
     return _deterministic
 
 
-def fused_backward_supported(Q) -> bool:
-    return Q.shape[-1] == 64
+# Head dim 128: fused kernel (csrc/fa_bwd_fused128.cuh) for the plain operator (no range masks, no dropout).
+_fused128 = os.environ.get("FA_SM100_FUSED128", "0") not in ("", "0")
+
+
+def set_fused128(flag: bool) -> bool:
+    """Use the fused single-pass backward at head dim 128 too (plain operator only); returns the previous setting."""
+    global _fused128
+    prev, _fused128 = _fused128, bool(flag)
+    if _native is not None and hasattr(_native, "set_fused128"):
+        _native.set_fused128(_fused128)
+    return prev
+
+
+def fused_backward_supported(Q, ranges=None, dropout_p=0.0) -> bool:
+    D = Q.shape[-1]
+    return D == 64 or (D == 128 and _fused128 and ranges is None and not dropout_p)
 
 
 BWD_FUSED, BWD_CONVERT = 8, 16
@@ -292,7 +307,7 @@ def flash_attention_backward(Q, K, V, O, dO, LSE, is_causal, sm_scale=None, rang
     B, H, S_q, D = Q.shape
     dQ, dK, dV = _empty_like_kernel(Q), _empty_like_kernel(K), _empty_like_kernel(V)      # reference :71-73
     delta = torch.empty((B, H, S_q), dtype=torch.float32, device=Q.device)
-    if fused_backward_supported(Q) and not _deterministic:
+    if fused_backward_supported(Q, ranges, dropout_p) and not _deterministic:
         flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale, None, 0, ranges, dropout_p,
                                        dropout_seed)
     else:

@@ -54,8 +54,29 @@ def bench(B, H, S, causal, D=64):
             "two_kernel_tflops": round(fl / t2 / 1e9, 1), "fused_tflops": round(fl / tf / 1e9, 1)}
 
 
+SHAPES128 = [(1, 1, 1, 128, 128, False), (1, 2, 2, 256, 256, True), (2, 4, 4, 512, 512, False), (1, 2, 2, 200, 300, False),
+             (1, 3, 3, 333, 333, True), (2, 8, 2, 320, 448, False), (2, 8, 2, 320, 320, True), (1, 2, 2, 1, 77, False),
+             (2, 4, 4, 2048, 2048, True), (1, 2, 2, 8192, 8192, True), (1, 160, 160, 1024, 1024, True)]
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "check128":          # one subprocess per shape: a trapped kernel poisons only its own CUDA context
+        import subprocess
+        for i in range(len(SHAPES128) + 1):
+            r = subprocess.run([sys.executable, __file__, "one128", str(i)], capture_output=True, text=True, timeout=180)
+            print(r.stdout.strip() or json.dumps({"shape_index": i, "rc": r.returncode, "stderr": r.stderr[-600:]}), flush=True)
+        sys.exit(0)
+    if what == "one128":
+        i = int(sys.argv[2])
+        if i < len(SHAPES128):
+            print(json.dumps(run(*SHAPES128[i], D=128)), flush=True)
+        else:
+            print(json.dumps(run(2, 4, 4, 512, 512, True, torch.float16, D=128)), flush=True)
+        sys.exit(0)
+    if what == "bench128":
+        for args in [(4, 16, 4096, False), (2, 32, 8192, True), (4, 8, 1024, True), (16, 32, 8192, True)]:
+            print(json.dumps(bench(*args, D=128)), flush=True)
+        sys.exit(0)
     if what in ("all", "check"):
         for args in [(1, 1, 1, 128, 128, False), (1, 2, 2, 256, 256, True), (2, 4, 4, 512, 512, False), (1, 2, 2, 200, 300, False),
                      (1, 3, 3, 333, 333, True), (2, 8, 2, 320, 448, False), (2, 8, 2, 320, 320, True), (1, 2, 2, 1, 77, False),

@@ -58,10 +58,10 @@ def test_argument_validation_without_gpu(lib):
     assert lib.fa_sm100_fwd_strided(p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, bad, None) == -8
     assert lib.fa_sm100_fwd_strided(p, p, p, p, p, 1, 6, 4, 128, 128, 64, 1, 0, 0.0, None, None) == -4   # Hk must divide H
     fused = lambda D=64, acc=p: lib.fa_sm100_bwd_fused(p, p, p, p, p, p, p, p, p, p, acc, 1, 2, 2, 128, 128, D, 1, 1, 0.0, None, None, 0)
-    assert fused(D=128) == -3 and b"fused" in lib.fa_last_error()          # TMEM budget: head dim 64 only
+    assert fused(D=96) == -3 and b"head dim" in lib.fa_last_error()        # fused kernels exist for head dims 64 and 128
     assert fused(acc=None) == -1
     assert lib.fa_sm100_bwd_fused_workspace(2, 4, 256, 64) == 2 * 4 * 256 * 64 * 4
-    assert lib.fa_sm100_bwd_fused_workspace(2, 4, 256, 128) == 0
+    assert lib.fa_sm100_bwd_fused_workspace(2, 4, 256, 128) == 2 * 4 * 256 * 128 * 4 and lib.fa_sm100_bwd_fused_workspace(2, 4, 256, 96) == 0
     # range masks: lo / hi arrays come in pairs (quadruples for the backward)
     assert lib.fa_sm100_fwd_ranges(p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, None, p, None, None) == -1
     assert lib.fa_sm100_bwd_ranges(p, p, p, p, p, p, p, p, p, p, 1, 2, 2, 128, 128, 64, 1, 0, 0.0, None, p, p, p, None, None, 7) == -1

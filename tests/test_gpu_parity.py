@@ -334,6 +334,39 @@ def test_fused_backward_matches_two_kernel_backward():
             assert _close(fused[1].cpu(), rdK) and _close(fused[2].cpu(), rdV)
 
 
+def test_fused128_backward_matches_two_kernel_backward_and_oracle():
+    """Head dim 128: the opt-in fused single-pass backward (csrc/fa_bwd_fused128.cuh, FA_SM100_FUSED128=1 / set_fused128) against
+    the default two-kernel backward on the same inputs.  Same exponentials and the same MMA order per kv tile, so dK and dV
+    are BITWISE equal; dQ differs only by its fp32 summation order over kv tiles (TMA reduce-add) and the final rounding.
+    Ragged shapes, S_q != S_k, GQA, both dtypes, a long causal sequence; every gradient also against the fp64 closed form."""
+    from flashattn_b200 import interface as I
+    for (B, H, Hk, Sq, Sk, causal, dt) in ((1, 1, 1, 128, 128, False, torch.bfloat16), (2, 4, 4, 512, 512, True, torch.bfloat16),
+                                           (1, 3, 3, 333, 333, True, torch.float16), (2, 8, 2, 320, 448, False, torch.bfloat16),
+                                           (1, 2, 2, 1, 77, False, torch.bfloat16), (1, 2, 2, 200, 300, False, torch.float16),
+                                           (1, 2, 1, 2176, 2176, True, torch.bfloat16)):
+        g = torch.Generator().manual_seed(Sq + Sk + H)
+        Q = torch.randn(B, H, Sq, 128, generator=g).to(dt); dO = torch.randn(B, H, Sq, 128, generator=g).to(dt)
+        K = torch.randn(B, Hk, Sk, 128, generator=g).to(dt); V = torch.randn(B, Hk, Sk, 128, generator=g).to(dt)
+        Qc, Kc, Vc, dOc = (t.cuda() for t in (Q, K, V, dO))
+        O, LSE = fa.flash_attention_forward(Qc, Kc, Vc, causal)
+        two = fa.flash_attention_backward(Qc, Kc, Vc, O, dOc, LSE, causal)
+        prev = I.set_fused128(True)
+        try:
+            assert I.fused_backward_supported(Qc)
+            fused = fa.flash_attention_backward(Qc, Kc, Vc, O, dOc, LSE, causal)
+        finally:
+            I.set_fused128(prev)
+        assert torch.equal(fused[1], two[1]) and torch.equal(fused[2], two[2]), (Sq, Sk)
+        assert _close(fused[0], two[0], 8e-3, 8e-3) and (fused[0].float() - two[0].float()).abs().mean() < 2e-4
+        G = H // Hk
+        _, _, rdQ, rdK, rdV = orc.closed_form(Q, K.repeat_interleave(G, dim=1), V.repeat_interleave(G, dim=1), dO, causal)
+        assert _close(fused[0].cpu(), rdQ), (Sq, Sk)
+        if G == 1:
+            assert _close(fused[1].cpu(), rdK) and _close(fused[2].cpu(), rdV)
+    import flashattn_b200._cabi as cabi
+    assert cabi.last_hang() is None
+
+
 @pytest.mark.parametrize("shape", [(1, 3, 200, 300, 64), (2, 2, 333, 129, 128), (1, 2, 1, 77, 64), (1, 1, 640, 384, 128)],
                          ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("causal", [False, True], ids=["full", "causal"])
