@@ -477,9 +477,12 @@ def main():
 
 
 def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks, steps=3):
-    """BASELINE config C5 (B=1 H=32 N=131072 D=128 bf16 causal) sequence-sharded over the ranks: zigzag ring, K/V blocks and the
-    fp32 dK/dV accumulators over NCCL P2P (flashattn_b200.sharding).  Timed like the headline (CUDA events per step, max over
-    ranks); one extra instrumented step gives the per-hop split."""
+    """BASELINE config C5 (B=1 H=32 N=131072 D=128 bf16 causal) sequence-sharded (zigzag) over the ranks, both variants of
+    flashattn_b200.sharding, timed like the headline (CUDA events per step, max over ranks):
+      ring    K/V blocks and the fp32 dK/dV accumulators travel neighbour to neighbour over NCCL send/recv, P hops
+      gather  NVSwitch variant: K/V all-gathered once per head group, ONE range-masked launch per group, dK/dV partials
+              all-to-all'ed to their owners and summed in fp32
+    One extra instrumented step per variant gives the per-hop / per-group split.  `value` is the faster variant's."""
     import torch
     import flashattn_b200.sharding as sh
     B, H, N, D = C5
@@ -487,38 +490,63 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     q, k, v, do = (torch.randn(B, H, S2, D, device=dev, generator=g, dtype=torch.float32).to(dtype) for _ in range(4))
     q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
-
-    def step(timeline=None):
-        O = sh.ring_flash_attention(q, k, v, None, None, None, timeline)
-        O.backward(do)
-        q.grad = None; k.grad = None; v.grad = None
-
-    step(); step()                                            # communicator set-up and allocator warm-up
-    barrier()
-    ts = []
-    for _ in range(steps):
-        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
-        barrier(); s.record(); step(); e.record(); torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e))
-    ms = max_over_ranks(sum(ts) / len(ts))
-    tl = []
-    barrier(); step(tl); torch.cuda.synchronize()
-    ev = dict(tl)
-    hops = []
-    for ph in ("fwd", "bwd"):
-        for s_ in range(world):
-            a_, b_, c_ = ev[f"{ph}{s_}:start"], ev[f"{ph}{s_}:compute_end"], ev[f"{ph}{s_}:end"]
-            hops.append(dict(hop=f"{ph}{s_}", compute_ms=a_.elapsed_time(b_), wait_and_accumulate_ms=b_.elapsed_time(c_)))
     flops = 3.5 * 4 * B * H * N * N * D / 2
-    val = flops / (ms * 1e-3) / 1e12
-    return dict(workload=f"C5: B={B} H={H} N={N} D={D} causal fwd+bwd, zigzag sequence ring over {world} GPUs (N/{world} = {S2} rows per rank)",
-                ms_per_step=ms, value=val, unit="TFLOPS", per_gpu_tflops=val / world,
-                per_gpu_frac_of_measured_peak=val / world / peak["bf16_burst"],
-                per_gpu_frac_of_measured_sustained_peak=val / world / peak["bf16_sustained"],
-                hops_rank0=hops,
-                compute_ms_rank0=sum(h["compute_ms"] for h in hops), wait_and_accumulate_ms_rank0=sum(h["wait_and_accumulate_ms"] for h in hops),
-                note="compute = the hop's attention kernels + (O,LSE) merges / dQ adds on the compute stream; wait_and_accumulate = waiting for the "
-                     "next K/V block and the incoming dK/dV accumulators (NCCL P2P, posted before the hop's compute) + the fp32 adds into them")
+
+    def run(fn):
+        def step(timeline=None):
+            O = fn(q, k, v, timeline)
+            O.backward(do)
+            q.grad = None; k.grad = None; v.grad = None
+        step(); step()                                            # communicator set-up and allocator warm-up
+        barrier()
+        ts = []
+        for _ in range(steps):
+            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+            barrier(); s.record(); step(); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ms = max_over_ranks(sum(ts) / len(ts))
+        tl = []
+        barrier(); step(tl); torch.cuda.synchronize()
+        val = flops / (ms * 1e-3) / 1e12
+        return dict(ms_per_step=ms, value=val, unit="TFLOPS", per_gpu_tflops=val / world,
+                    per_gpu_frac_of_measured_peak=val / world / peak["bf16_burst"],
+                    per_gpu_frac_of_measured_sustained_peak=val / world / peak["bf16_sustained"]), tl
+
+    out = dict(workload=f"C5: B={B} H={H} N={N} D={D} causal fwd+bwd, zigzag sequence sharding over {world} GPUs (N/{world} = {S2} rows per rank)",
+               variants={})
+    try:
+        r, tl = run(lambda q_, k_, v_, t: sh.ring_flash_attention(q_, k_, v_, None, None, None, t))
+        ev = dict(tl); hops = []
+        for ph in ("fwd", "bwd"):
+            for s_ in range(world):
+                a_, b_, c_ = ev[f"{ph}{s_}:start"], ev[f"{ph}{s_}:compute_end"], ev[f"{ph}{s_}:end"]
+                hops.append(dict(hop=f"{ph}{s_}", compute_ms=a_.elapsed_time(b_), wait_and_accumulate_ms=b_.elapsed_time(c_)))
+        r.update(hops_rank0=hops, compute_ms_rank0=sum(h["compute_ms"] for h in hops),
+                 wait_and_accumulate_ms_rank0=sum(h["wait_and_accumulate_ms"] for h in hops),
+                 note="compute = the hop's attention kernels + (O,LSE) merges / dQ adds on the compute stream; wait_and_accumulate = waiting for "
+                      "the next K/V block and the incoming dK/dV accumulators (NCCL P2P, posted before the hop's compute) + the fp32 adds")
+        out["variants"]["ring"] = r
+    except Exception as e:
+        out["variants"]["ring"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    try:
+        r, tl = run(lambda q_, k_, v_, t: sh.gather_flash_attention(q_, k_, v_, None, None, 4, t))
+        marks = []
+        for (n0, e0), (n1, e1) in zip(tl[:-1], tl[1:]):
+            marks.append(dict(segment=f"{n0} -> {n1}", ms=e0.elapsed_time(e1)))
+        r.update(segments_rank0=marks,
+                 note="4 head groups; all K/V all-gathers are posted before the first group's kernels; each group's dK/dV all-to-all is posted "
+                      "right after the group's backward kernels; the last segment (bwd:group3 -> bwd:end) is the exposed tail: waiting for "
+                      "the all-to-alls + the fp32 sums of the partials")
+        out["variants"]["gather"] = r
+    except Exception as e:
+        out["variants"]["gather"] = {"error": repr(e)[:300]}
+    ok = {n: r for n, r in out["variants"].items() if "value" in r}
+    if ok:
+        best = min(ok, key=lambda n: ok[n]["ms_per_step"])
+        out.update(variant=best, **{k_: ok[best][k_] for k_ in ("ms_per_step", "value", "unit", "per_gpu_tflops", "per_gpu_frac_of_measured_peak",
+                                                              "per_gpu_frac_of_measured_sustained_peak")})
+    return out
 
 
 if __name__ == "__main__":

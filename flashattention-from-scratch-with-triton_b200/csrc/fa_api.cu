@@ -46,9 +46,11 @@ EncodeTiledFn get_encode() {
 // [B, H, S, D] 16-bit tensor as a 4-D map with explicit batch / head / row strides (never flattened across heads,
 // so a partial tile cannot touch the next head — fixes the reference's flattened-descriptor overrun).
 // Box = [1][1][box_rows][64 columns], SWIZZLE_128B; out-of-range rows read as zero and are not written.
+thread_local int t_last_curesult = 0;       // CUresult of the last failed cuTensorMapEncodeTiled of this thread (error messages)
+
 bool make_map(CUtensorMap* m, const void* ptr, int B, int H, int S, int D, const RowStrides& st, int dtype, int box_rows) {
     EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
+    if (!enc) { t_last_curesult = -1; return false; }
     cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)st.r * 2, (cuuint64_t)st.h * 2, (cuuint64_t)st.b * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
@@ -57,6 +59,7 @@ bool make_map(CUtensorMap* m, const void* ptr, int B, int H, int S, int D, const
                      4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) t_last_curesult = (int)r;
     return r == CUDA_SUCCESS;
 }
 
@@ -107,6 +110,16 @@ int device_info(DeviceInfo** out) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
     if (dev < 0 || dev >= kMaxDevices) return fail(FA_ERR_DEVICE, "device ordinal %d out of range", dev);
+    // cuTensorMapEncodeTiled is a DRIVER call and needs a current context.  A thread that has only ever seen cached allocations
+    // (PyTorch's autograd worker running the first backward of a process) has none yet: cudaGetDevice does not bind the primary
+    // context, and the encode fails with CUDA_ERROR_INVALID_CONTEXT (201).  Bind it once per thread and device.
+    static thread_local int t_ctx_dev = -1;
+    if (t_ctx_dev != dev) {
+        e = cudaSetDevice(dev);
+        if (e == cudaSuccess) e = cudaFree(nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "binding the primary context of the device to this thread");
+        t_ctx_dev = dev;
+    }
     DeviceInfo& d = g_dev[dev];
     if (!d.ready.load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lk(g_dev_mu);
@@ -409,11 +422,14 @@ int fa_sm100_bwd_fused_opt(const void* q, const void* k, const void* v, const vo
     cudaStream_t st = (cudaStream_t)stream;
     const int BH = B * H;
     CUtensorMap mq, mk, mv, mdo, mdk, mdv, macc;
-    if (!make_map(&mq, q, B, H, Sq, D, s_q, dtype, 128) || !make_map(&mk, k, B, Hk, Sk, D, s_k, dtype, 128) ||
-        !make_map(&mv, v, B, Hk, Sk, D, s_v, dtype, 128) || !make_map(&mdo, dout, B, H, Sq, D, s_do, dtype, 128) ||
-        !make_map(&mdk, dk, B, Hk, Sk, D, s_dk, dtype, 128) || !make_map(&mdv, dv, B, Hk, Sk, D, s_dv, dtype, 128) ||
-        !make_map_acc(&macc, dq_acc, BH, Sq, D))
-        return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (B=%d H=%d Sq=%d Sk=%d D=%d)", B, H, Sq, Sk, D);
+    {
+        const char* bad = !make_map(&mq, q, B, H, Sq, D, s_q, dtype, 128) ? "q" : !make_map(&mk, k, B, Hk, Sk, D, s_k, dtype, 128) ? "k" :
+                          !make_map(&mv, v, B, Hk, Sk, D, s_v, dtype, 128) ? "v" : !make_map(&mdo, dout, B, H, Sq, D, s_do, dtype, 128) ? "dout" :
+                          !make_map(&mdk, dk, B, Hk, Sk, D, s_dk, dtype, 128) ? "dk" : !make_map(&mdv, dv, B, Hk, Sk, D, s_dv, dtype, 128) ? "dv" :
+                          !make_map_acc(&macc, dq_acc, BH, Sq, D) ? "dq_acc" : nullptr;
+        if (bad) return fail(FA_ERR_DRIVER, "cuTensorMapEncodeTiled failed for %s with CUresult %d (B=%d H=%d Hk=%d Sq=%d Sk=%d D=%d, q=%p strides b/h/r %lld/%lld/%lld)",
+                             bad, t_last_curesult, B, H, Hk, Sq, Sk, D, q, s_q.b, s_q.h, s_q.r);
+    }
     // delta = rowsum(dO o O) and, in the same pass, zeros into the dQ accumulator
     int rc = 0;
     if (parts & FA_BWD_DELTA) {

@@ -297,6 +297,191 @@ def ring_flash_attention(q, k, v, group=None, comm=None, splits=None, timeline=N
     return RingFlashAttentionFunction.apply(q, k, v, group, comm, splits, timeline)
 
 
+# ------------------------------------------------------------------------------------------------
+# NVSwitch variant: gather K/V once, one range-masked launch per head group, scatter-add dK/dV
+# ------------------------------------------------------------------------------------------------
+# The ring above is the NVLink-ring schedule (P hops, send/recv to the neighbours).  On an NVSwitch box every GPU reaches every peer
+# at full bandwidth and 180 GB of HBM hold the whole K/V of a long sequence many times over (C5: 2 x 1 GiB), so the hop structure
+# buys nothing: K and V are all-gathered ONCE (per head group, so the transfer of group g+1 runs under the kernels of group g),
+# put in global order, and each rank runs the single-GPU kernels ONCE per group on "local queries x all keys" with a Ranges mask
+# (query at global position p sees keys [0, p]): no per-hop launches, no (O, LSE) merges, no fp32 accumulators on the wire, and the
+# dynamic tile scheduler balances the causal work inside the launch.  The backward's dK/dV partials (16-bit, what the kernel
+# writes) go to their owner ranks with one all-to-all per group and are summed there in fp32.
+
+
+def zigzag_ranges(rank: int, world: int, c: int, B: int, device) -> "object":
+    """Ranges for the zigzag-local query rows (chunks `rank` and 2P-1-rank, c rows each) against the GLOBALLY ordered keys."""
+    from .interface import Ranges
+    a, b = zigzag_chunks(rank, world)
+    i = torch.arange(c, device=device)
+    gpos = torch.cat([a * c + i, b * c + i])                       # global position of local row
+    row_hi = (gpos + 1)[None].expand(B, 2 * c)
+    row_lo = torch.zeros_like(row_hi)
+    j = torch.arange(2 * c * world, device=device)
+    col_lo = torch.where(j < a * c, 0, torch.where(j < (a + 1) * c, j - a * c, torch.where(j < b * c, c, torch.where(
+        j < (b + 1) * c, c + j - b * c, 2 * c))))[None].expand(B, -1)
+    col_hi = torch.full_like(col_lo, 2 * c)
+    return Ranges(row_lo, row_hi, col_lo, col_hi)
+
+
+def _to_global(buf: torch.Tensor) -> torch.Tensor:
+    """[P, B, h, 2c, D] (rank-major, each rank's zigzag pair) -> [B, h, 2Pc, D] in global sequence order."""
+    P, B, h, S2, D = buf.shape
+    c = S2 // 2
+    out = torch.empty(B, h, 2 * P, c, D, dtype=buf.dtype, device=buf.device)
+    b5 = buf.view(P, B, h, 2, c, D)
+    out[:, :, :P] = b5[:, :, :, 0].permute(1, 2, 0, 3, 4)
+    out[:, :, P:] = b5[:, :, :, 1].flip(0).permute(1, 2, 0, 3, 4)
+    return out.view(B, h, 2 * P * c, D)
+
+
+def _from_global(t: torch.Tensor, P: int) -> torch.Tensor:
+    """Inverse of _to_global: [B, h, 2Pc, D] -> [P, B, h, 2c, D]."""
+    B, h, N, D = t.shape
+    c = N // (2 * P)
+    t5 = t.view(B, h, 2 * P, c, D)
+    out = torch.empty(P, B, h, 2, c, D, dtype=t.dtype, device=t.device)
+    out[:, :, :, 0] = t5[:, :, :P].permute(2, 0, 1, 3, 4)
+    out[:, :, :, 1] = t5[:, :, P:].flip(2).permute(2, 0, 1, 3, 4)
+    return out.view(P, B, h, 2 * c, D)
+
+
+class GatherOps:
+    """Local kernels of the gather variant = the sm_100a library with a Ranges mask."""
+
+    def fwd(self, q, k, v, ranges):
+        from .interface import flash_attention_forward
+        return flash_attention_forward(q, k, v, False, None, ranges)
+
+    def bwd(self, q, k, v, o, do, lse, ranges):
+        from .interface import flash_attention_backward
+        return flash_attention_backward(q, k, v, o, do, lse, False, None, ranges)
+
+
+class DistCollectives:
+    """all_gather / all_to_all over torch.distributed (NCCL over NVSwitch on GPUs, gloo on CPU ranks), asynchronous."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group); self.rank = dist.get_rank(group)
+
+    def all_gather(self, t):
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        if self.world == 1:
+            out[0].copy_(t); return out, None
+        return out, self.dist.all_gather_into_tensor(out.view(-1), t.reshape(-1), group=self.group, async_op=True)
+
+    def all_to_all(self, send):
+        recv = torch.empty_like(send)
+        if self.world == 1:
+            recv.copy_(send); return recv, None
+        if send.is_cuda:
+            return recv, self.dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group, async_op=True)
+        ins = list(send.unbind(0)); outs = list(recv.unbind(0))            # gloo has no all_to_all_single
+        self.dist.all_to_all(outs, ins, group=self.group) if self.dist.get_backend(self.group) != "gloo" else _gloo_all_to_all(self.dist, outs, ins, self.group)
+        return recv, None
+
+
+def _gloo_all_to_all(dist, outs, ins, group):
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ops = []
+    for r in range(world):
+        if r == rank:
+            outs[r].copy_(ins[r])
+        else:
+            ops.append(dist.P2POp(dist.isend, ins[r].contiguous(), r, group)); ops.append(dist.P2POp(dist.irecv, outs[r], r, group))
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+
+
+def _head_groups(Hk: int, G: int, n: int):
+    n = max(1, min(n, Hk)); per = -(-Hk // n)
+    return [(slice(h * G, min(h + per, Hk) * G), slice(h, min(h + per, Hk))) for h in range(0, Hk, per)]
+
+
+def gather_attention_forward(q, k, v, group=None, ops=None, coll=None, groups=4, timeline=None):
+    """Causal attention over the global sequence; q, k, v are this rank's zigzag-local [B,H,2c,D] / [B,Hk,2c,D] tensors.
+    Returns (O, LSE, saved) where `saved` carries the gathered K/V (global order, per head group) and the Ranges for the backward."""
+    ops = ops or GatherOps()
+    coll = coll or DistCollectives(group)
+    P, rank = coll.world, coll.rank
+    B, H, S2, D = q.shape
+    Hk = k.shape[1]; G = H // Hk
+    c = S2 // 2
+    ranges = zigzag_ranges(rank, P, c, B, q.device)
+    hg = _head_groups(Hk, G, groups)
+    _mark(timeline, q, "fwd:start")
+    pend = [(coll.all_gather(k[:, ks].contiguous()), coll.all_gather(v[:, ks].contiguous())) for _, ks in hg]   # all posted up front
+    O = torch.empty_like(q); LSE = torch.empty(B, H, S2, dtype=torch.float32, device=q.device)
+    kv_glob = []
+    for gi, (qs, ks) in enumerate(hg):
+        (kb, kw), (vb, vw) = pend[gi]
+        for w in (kw, vw):
+            if w is not None:
+                w.wait()
+        Kg, Vg = _to_global(kb), _to_global(vb)
+        pend[gi] = None
+        Og, Lg = ops.fwd(q[:, qs], Kg, Vg, ranges)
+        O[:, qs] = Og; LSE[:, qs] = Lg
+        kv_glob.append((Kg, Vg))
+        _mark(timeline, q, f"fwd:group{gi}")
+    return O, LSE, (kv_glob, ranges, hg)
+
+
+def gather_attention_backward(q, O, dO, LSE, saved, group=None, ops=None, coll=None, timeline=None):
+    """Gradients for gather_attention_forward.  dQ is local; the dK / dV partials of every key (16-bit, global order) are sent to
+    the key's owner (one all-to-all per head group, posted as soon as the group's kernels are enqueued) and summed there in fp32."""
+    ops = ops or GatherOps()
+    coll = coll or DistCollectives(group)
+    P = coll.world
+    kv_glob, ranges, hg = saved
+    dq = torch.empty_like(q)
+    Hk = sum(ks.stop - ks.start for _, ks in hg)
+    B, H, S2, D = q.shape
+    dk = torch.empty(B, Hk, S2, D, dtype=q.dtype, device=q.device); dv = torch.empty_like(dk)
+    _mark(timeline, q, "bwd:start")
+    pend = []
+    for gi, (qs, ks) in enumerate(hg):
+        Kg, Vg = kv_glob[gi]
+        dqg, dKg, dVg = ops.bwd(q[:, qs], Kg, Vg, O[:, qs], dO[:, qs], LSE[:, qs], ranges)
+        dq[:, qs] = dqg
+        pend.append((coll.all_to_all(_from_global(dKg, P)), coll.all_to_all(_from_global(dVg, P))))
+        _mark(timeline, q, f"bwd:group{gi}")
+    for gi, (qs, ks) in enumerate(hg):
+        (kb, kw), (vb, vw) = pend[gi]
+        for w in (kw, vw):
+            if w is not None:
+                w.wait()
+        dk[:, ks] = kb.float().sum(0).to(q.dtype); dv[:, ks] = vb.float().sum(0).to(q.dtype)
+    _mark(timeline, q, "bwd:end")
+    return dq, dk, dv
+
+
+class GatherFlashAttentionFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, group=None, coll=None, groups=4, timeline=None):
+        assert q.dtype in (torch.float16, torch.bfloat16) and q.ndim == 4
+        q_ = q.contiguous()
+        O, LSE, saved = gather_attention_forward(q_, k, v, group, None, coll, groups, timeline)
+        ctx.save_for_backward(q_, O, LSE)
+        ctx.cp = (saved, group, coll, timeline)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        q, O, LSE = ctx.saved_tensors
+        saved, group, coll, timeline = ctx.cp
+        dq, dk, dv = gather_attention_backward(q, O, dO.contiguous(), LSE, saved, group, None, coll, timeline)
+        return dq, dk, dv, None, None, None, None
+
+
+def gather_flash_attention(q, k, v, group=None, coll=None, groups=4, timeline=None):
+    """Causal attention over a zigzag-sharded sequence, NVSwitch variant (see the section comment): same inputs / outputs as
+    ring_flash_attention."""
+    return GatherFlashAttentionFunction.apply(q, k, v, group, coll, groups, timeline)
+
+
 class ThreadRingComm:
     """In-process ring for P simulated ranks, one Python thread each, all on ONE device and one CUDA stream: the ring schedule
     and the real local kernels can be verified on a single GPU (tests/) or on CPU tensors.  exchange() snapshots the send
@@ -325,10 +510,39 @@ class ThreadRingComm:
         return _P()
 
 
-def run_virtual_ring(world, fn):
-    """Run fn(rank, comm) on `world` threads sharing a ThreadRingComm ring; returns the list of results (exceptions re-raised)."""
+class ThreadCollectives:
+    """In-process all_gather / all_to_all for P simulated ranks (threads of one process, one device, one CUDA stream): a
+    thread barrier orders the enqueues, the stream orders the data."""
+
+    def __init__(self, rank, world, shared):
+        self.rank, self.world, self.shared = rank, world, shared
+
+    @staticmethod
+    def make(world):
+        import threading
+        shared = dict(barrier=threading.Barrier(world, timeout=120), slots=[None] * world)
+        return [ThreadCollectives(r, world, shared) for r in range(world)]
+
+    def _exchange(self, t, pick):
+        sh_ = self.shared
+        sh_["slots"][self.rank] = t
+        sh_["barrier"].wait()
+        out = pick(sh_["slots"])
+        sh_["barrier"].wait()                                # nobody overwrites a slot that is still being read
+        return out, None
+
+    def all_gather(self, t):
+        return self._exchange(t, lambda slots: torch.stack(list(slots)))
+
+    def all_to_all(self, send):
+        return self._exchange(send, lambda slots: torch.stack([slots[r][self.rank] for r in range(self.world)]))
+
+
+def run_virtual_ring(world, fn, make=None):
+    """Run fn(rank, comm) on `world` threads sharing a ThreadRingComm ring (or the comm objects of `make(world)`); returns the list
+    of results (exceptions re-raised)."""
     import threading
-    comms = ThreadRingComm.make(world)
+    comms = (make or ThreadRingComm.make)(world)
     out, err = [None] * world, [None] * world
 
     def work(r):

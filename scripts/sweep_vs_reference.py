@@ -43,7 +43,10 @@ def main():
                 for S in map(int, a.seqs.split(",")):
                     cfg = dict(B=a.B, H=a.H, Sq=S, Sk=S, D=D, causal=causal)
                     row = dict(cfg)
-                    row["ours_bf16"] = ref_runner.bench_fn(fa.flash_attention, dtype=torch.bfloat16, **cfg)
+                    try:
+                        row["ours_bf16"] = ref_runner.bench_fn(fa.flash_attention, dtype=torch.bfloat16, **cfg)
+                    except Exception as e:
+                        row["ours_bf16"] = dict(error=repr(e)[:300])
                     if ref_fn is not None:
                         try:
                             row["reference_fp16"] = ref_runner.bench_fn(ref_fn, dtype=torch.float16, **cfg)
@@ -61,7 +64,7 @@ def main():
     for r in rows:
         o, rf, sd = r["ours_bf16"], r.get("reference_fp16", {}), r.get("sdpa_flash_bf16", {})
         cell = lambda d, k: f"{d[k]:.0f}" if k in d else "-"
-        ratio = lambda k: f"{o[k] / rf[k]:.2f}" if k in rf else "-"
+        ratio = lambda k: f"{o[k] / rf[k]:.2f}" if (k in rf and k in o) else "-"
         print(f"| {r['D']} | {'yes' if r['causal'] else 'no'} | {r['Sq']} | {cell(o, 'tflops_fwd')} | {cell(rf, 'tflops_fwd')} | {ratio('tflops_fwd')} "
               f"| {cell(o, 'tflops_bwd')} | {cell(rf, 'tflops_bwd')} | {ratio('tflops_bwd')} "
               f"| {cell(o, 'tflops_fwd_bwd')} | {cell(rf, 'tflops_fwd_bwd')} | {ratio('tflops_fwd_bwd')} | {cell(sd, 'tflops_fwd_bwd')} |")

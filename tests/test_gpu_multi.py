@@ -63,6 +63,41 @@ def test_virtual_ring_on_one_gpu(world, D, Hk):
         assert torch.allclose(full, one.detach().cpu().float(), atol=2 * atol, rtol=2e-2), name   # two 16-bit results, each within the contract
 
 
+@pytest.mark.parametrize("world,D,Hk,groups", [(2, 128, 4, 2), (4, 64, 4, 1), (8, 128, 2, 2)], ids=["P2_d128", "P4_d64", "P8_d128_gqa"])
+def test_virtual_gather_variant_on_one_gpu(world, D, Hk, groups):
+    """The NVSwitch variant (sharding.gather_attention_forward / _backward: all-gather K/V, ONE range-masked launch per head group,
+    all-to-all + fp32 sum of the dK/dV partials) with the REAL kernels for P simulated ranks on one GPU (threads joined by
+    sharding.ThreadCollectives).  Against the fp64 closed form (contract tolerance) and the one-shot kernel."""
+    import math
+    import flashattn_b200 as fa
+    import flashattn_b200.sharding as sh
+    B, H, c = 1, 4, 256
+    S = 2 * c * world
+    g = torch.Generator().manual_seed(80 + world)
+    Q = torch.randn(B, H, S, D, generator=g).bfloat16(); dO = torch.randn(B, H, S, D, generator=g).bfloat16()
+    K = torch.randn(B, Hk, S, D, generator=g).bfloat16(); V = torch.randn(B, Hk, S, D, generator=g).bfloat16()
+
+    def rank_fn(rank, coll):
+        torch.cuda.set_device(0)
+        q, k, v, do = (sh.zigzag_split(t, rank, world).cuda() for t in (Q, K, V, dO))
+        O, LSE, saved = sh.gather_attention_forward(q, k, v, None, None, coll, groups)
+        dq, dk, dv = sh.gather_attention_backward(q, O, do, LSE, saved, None, None, coll)
+        return O.cpu(), dq.cpu(), dk.cpu(), dv.cpu()
+
+    outs = sh.run_virtual_ring(world, rank_fn, sh.ThreadCollectives.make)
+    torch.cuda.synchronize()
+    G = H // Hk
+    rO, _, rdQ, rdKe, rdVe = orc.closed_form(Q, K.repeat_interleave(G, dim=1), V.repeat_interleave(G, dim=1), dO, True)
+    rdK = rdKe.reshape(B, Hk, G, S, D).sum(2); rdV = rdVe.reshape(B, Hk, G, S, D).sum(2)
+    q1, k1, v1 = (t.cuda().requires_grad_(True) for t in (Q, K, V))
+    O1 = fa.flash_attention(q1, k1, v1, True); O1.backward(dO.cuda())
+    for i, (name, ref, one) in enumerate((("O", rO, O1), ("dQ", rdQ, q1.grad), ("dK", rdK, k1.grad), ("dV", rdV, v1.grad))):
+        full = sh.zigzag_merge([o[i] for o in outs], dim=2).float()
+        atol = 1e-2 * (math.sqrt(G) if name in ("dK", "dV") else 1.0)
+        assert torch.allclose(full, ref.float(), atol=atol, rtol=1e-2), (name, (full - ref.float()).abs().max().item())
+        assert torch.allclose(full, one.detach().cpu().float(), atol=2 * atol, rtol=2e-2), name
+
+
 def test_virtual_ring_c5_head_vs_one_shot_and_truth():
     """One head of BASELINE config C5 (N = 131072, D = 128, bf16, causal) as a ring of 8 simulated ranks on one GPU against the
     one-shot kernel on the whole sequence, and both against fp32 truth on every element (contract tolerance)."""

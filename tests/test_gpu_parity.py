@@ -334,6 +334,45 @@ def test_fused_backward_matches_two_kernel_backward():
             assert _close(fused[1].cpu(), rdK) and _close(fused[2].cpu(), rdV)
 
 
+def test_first_call_on_a_thread_without_cuda_context():
+    """cuTensorMapEncodeTiled is a driver call and needs a current context; a thread that has made no CUDA runtime call yet (the
+    autograd worker running the first backward of a process, with every output coming from the caching allocator) has none.  The
+    library binds the primary context itself (csrc/fa_api.cu::device_info): every entry point must work as the FIRST CUDA-related
+    call of a fresh thread, with all tensors allocated beforehand.  (Found by the sweep: CUresult 201 on its first backward.)"""
+    import threading
+    from flashattn_b200 import interface as I
+    for D in (64, 128):
+        Q, K, V, dO = (t.cuda() for t in orc.make_inputs(1, 2, 256, 256, D, torch.bfloat16, seed=3))
+        O, LSE = fa.flash_attention_forward(Q, K, V, True)
+        ref = fa.flash_attention_backward(Q, K, V, O, dO, LSE, True)
+        dQ, dK, dV = (torch.zeros_like(t) for t in (Q, K, V))
+        delta = torch.empty(1, 2, 256, dtype=torch.float32, device="cuda"); acc = torch.empty(1, 2, 256, D, dtype=torch.float32, device="cuda")
+        O2 = torch.empty_like(O); L2 = torch.empty_like(LSE)
+        torch.cuda.synchronize()
+        err = []
+
+        def work():
+            try:
+                lib = __import__("flashattn_b200._cabi", fromlist=["load"]).load()
+                st = torch.cuda.current_stream().cuda_stream
+                rc = lib.fa_sm100_fwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O2.data_ptr(), L2.data_ptr(), 1, 2, 256, 256, D, 1, 1, 0.0, st)
+                assert rc == 0, lib.fa_last_error()
+                if D == 64:
+                    I.flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, True, dq_acc=acc)
+                else:
+                    I.flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, True, 7)
+                torch.cuda.synchronize()
+            except BaseException as e:   # noqa: BLE001
+                err.append(e)
+
+        for first in ("bwd", "fwd+bwd"):
+            th = threading.Thread(target=work); th.start(); th.join()
+            assert not err, err
+        assert torch.equal(O2, O)
+        for x, y in zip((dQ, dK, dV), ref):
+            assert _close(x, y, 8e-3, 8e-3)
+
+
 def test_fused128_backward_matches_two_kernel_backward_and_oracle():
     """Head dim 128: the opt-in fused single-pass backward (csrc/fa_bwd_fused128.cuh, FA_SM100_FUSED128=1 / set_fused128) against
     the default two-kernel backward on the same inputs.  Same exponentials and the same MMA order per kv tile, so dK and dV

@@ -96,6 +96,81 @@ def test_virtual_ring_threads_equals_full_causal_attention(world, splits):
         assert (full - ref.float()).abs().max() < 2e-5, i
 
 
+class OracleGatherOps:
+    """Local 'kernels' of the gather variant on CPU ranks: exact fp32 attention under a Ranges row mask (same contract as
+    sharding.GatherOps)."""
+
+    @staticmethod
+    def _mask(ranges, Sk):
+        j = torch.arange(Sk)[None, None, :]
+        return (j >= ranges.row_lo[:, :, None]) & (j < ranges.row_hi[:, :, None])          # [B, Sq, Sk]
+
+    def fwd(self, q, k, v, ranges):
+        scale = 1 / math.sqrt(q.shape[-1])
+        S = (q.float() @ k.float().transpose(-1, -2) * scale).masked_fill(~self._mask(ranges, k.shape[2])[:, None], float("-inf"))
+        LSE = torch.logsumexp(S, -1)
+        return (torch.exp(S - LSE[..., None]) @ v.float()).to(q.dtype), LSE
+
+    def bwd(self, q, k, v, o, do, lse, ranges):
+        scale = 1 / math.sqrt(q.shape[-1])
+        qf, kf, vf, dof = q.float(), k.float(), v.float(), do.float()
+        S = (qf @ kf.transpose(-1, -2) * scale).masked_fill(~self._mask(ranges, k.shape[2])[:, None], float("-inf"))
+        P = torch.exp(S - lse[..., None])
+        delta = (o.float() * dof).sum(-1)
+        dS = P * (dof @ vf.transpose(-1, -2) - delta[..., None])
+        return (dS @ kf * scale).to(q.dtype), (dS.transpose(-1, -2) @ qf * scale).to(q.dtype), (P.transpose(-1, -2) @ dof).to(q.dtype)
+
+
+def _gather_worker(rank, world, port, S, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        Q, K, V, dO = orc.make_inputs(1, 4, S, S, 64, torch.float32, seed=4)
+        q, k, v, do = (sh.zigzag_split(t, rank, world) for t in (Q, K, V, dO))
+        sh.zigzag_ranges(rank, world, S // (2 * world), 1, "cpu").validate()               # row side == key side of the mask
+        ops = OracleGatherOps()
+        O, LSE, saved = sh.gather_attention_forward(q, k, v, None, ops, None, 2)
+        dq, dk, dv = sh.gather_attention_backward(q, O, do, LSE, saved, None, ops)
+        rO, rLSE, rdQ, rdK, rdV = orc.closed_form(Q, K, V, dO, True, dtype=torch.float64)
+        errs = [(a - sh.zigzag_split(b.float(), rank, world)).abs().max().item()
+                for a, b in ((O, rO), (dq, rdQ), (dk, rdK), (dv, rdV))]
+        errs.append((LSE - sh.zigzag_split(rLSE.float(), rank, world)).abs().max().item())
+        ret[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gather_variant_fwd_bwd_equals_full_causal_attention(world):
+    """NVSwitch variant (all-gather K/V, one range-masked launch per head group, all-to-all + fp32 sum of dK/dV) on gloo ranks."""
+    S = 64 * world
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_gather_worker, args=(world, _free_port(), S, ret), nprocs=world, join=True)
+        assert len(ret) == world
+        for r in range(world):
+            assert max(ret[r]) < 2e-5, (r, ret[r])
+
+
+def test_gather_variant_threads_equals_full_causal_attention():
+    """The same code driven by ThreadCollectives (8 simulated ranks as threads of one process)."""
+    world, S = 8, 256
+    Q, K, V, dO = orc.make_inputs(2, 3, S, S, 64, torch.float32, seed=10)
+    rO, rLSE, rdQ, rdK, rdV = orc.closed_form(Q, K, V, dO, True, dtype=torch.float64)
+
+    def rank_fn(rank, coll):
+        q, k, v, do = (sh.zigzag_split(t, rank, world) for t in (Q, K, V, dO))
+        ops = OracleGatherOps()
+        O, LSE, saved = sh.gather_attention_forward(q, k, v, None, ops, coll, 3)
+        return (O, LSE) + tuple(sh.gather_attention_backward(q, O, do, LSE, saved, None, ops, coll))
+
+    outs = sh.run_virtual_ring(world, rank_fn, sh.ThreadCollectives.make)
+    for i, ref in enumerate((rO, rLSE, rdQ, rdK, rdV)):
+        full = sh.zigzag_merge([o[i] for o in outs], dim=2)
+        assert (full - ref.float()).abs().max() < 2e-5, i
+
+
 def _shard_worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
