@@ -467,8 +467,8 @@ def main():
                                 "mma_utilisation": bw["mma_utilisation"], "executed_gemm_units": bw["executed_gemm_units"],
                                 "forward": {"kernel": "fa_fwd_kernel", "achieved": kb["fwd"]["achieved"], "frac": kb["fwd"]["frac"], "ms": kb["fwd"]["ms"],
                                             "traffic": ncu_traffic(wl_key, "fwd")}}
-        cb = cpu_baseline(Bg, H, S, D, causal)
-        line["cpu_baseline"] = cb
+        if world == 1:                                  # the CPU baseline is an N = 1 line item (rank 0's host cores)
+            line["cpu_baseline"] = cpu_baseline(Bg, H, S, D, causal)
     if rank == 0:
         real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
     if dist_on:
@@ -481,7 +481,8 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
     flashattn_b200.sharding, timed like the headline (CUDA events per step, max over ranks):
       ring    K/V blocks and the fp32 dK/dV accumulators travel neighbour to neighbour over NCCL send/recv, P hops
       gather  NVSwitch variant: K/V all-gathered once per head group, ONE range-masked launch per group, dK/dV partials
-              all-to-all'ed to their owners and summed in fp32
+              all-to-all'ed to their owners and summed in fp32; transports: NCCL collectives, or (gather_peer) NVLink peer memory
+              moved by the copy engines with stream-memory-op flags — no SM taken from the persistent attention kernels
     One extra instrumented step per variant gives the per-hop / per-group split.  `value` is the faster variant's."""
     import torch
     import flashattn_b200.sharding as sh
@@ -528,19 +529,27 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
         out["variants"]["ring"] = r
     except Exception as e:
         out["variants"]["ring"] = {"error": repr(e)[:300]}
-    torch.cuda.empty_cache()
-    try:
-        r, tl = run(lambda q_, k_, v_, t: sh.gather_flash_attention(q_, k_, v_, None, None, 4, t))
-        marks = []
-        for (n0, e0), (n1, e1) in zip(tl[:-1], tl[1:]):
-            marks.append(dict(segment=f"{n0} -> {n1}", ms=e0.elapsed_time(e1)))
-        r.update(segments_rank0=marks,
-                 note="4 head groups; all K/V all-gathers are posted before the first group's kernels; each group's dK/dV all-to-all is posted "
-                      "right after the group's backward kernels; the last segment (bwd:group3 -> bwd:end) is the exposed tail: waiting for "
-                      "the all-to-alls + the fp32 sums of the partials")
-        out["variants"]["gather"] = r
-    except Exception as e:
-        out["variants"]["gather"] = {"error": repr(e)[:300]}
+    max_ctas = int(os.environ.get("FA_CP_NCCL_MAX_CTAS", "8"))
+    # the peer-memory variant runs last: creating another NCCL communicator (make_cp_group) AFTER symmetric-memory buffers were
+    # exchanged on the default group ended in a launch failure on this stack (torch 2.11 / NCCL 2.28); the other order is fine
+    for name, grp in (("gather", "capped"), ("gather_default_nccl_ctas", None), ("gather_peer", "peer")):
+        torch.cuda.empty_cache()
+        try:
+            group = sh.make_cp_group(max_ctas) if grp == "capped" else None
+            coll = sh.PeerCollectives() if grp == "peer" else None
+            r, tl = run(lambda q_, k_, v_, t: sh.gather_flash_attention(q_, k_, v_, group, coll, None, t))
+            marks = []
+            for (n0, e0), (n1, e1) in zip(tl[:-1], tl[1:]):
+                marks.append(dict(segment=f"{n0} -> {n1}", ms=e0.elapsed_time(e1)))
+            r.update(segments_rank0=marks, head_groups=sh.default_head_groups(H),
+                     transport=("NVLink peer memory, copy engines, stream memory ops for the flags (sharding.PeerCollectives): no SMs" if grp == "peer"
+                                else f"NCCL all_gather / all_to_all, max_ctas = {max_ctas}" if grp == "capped" else "NCCL all_gather / all_to_all, default CTAs"),
+                     note="head groups [2,6,8,8,8]: all K/V all-gathers are posted before the first group's kernels (only the small first "
+                          "group's is exposed); the backward walks the groups in reverse, each group's dK/dV all-to-all is posted right after "
+                          "its kernels and summed (fp32) after the next group's kernels are enqueued; the last segment is the exposed tail")
+            out["variants"][name] = r
+        except Exception as e:
+            out["variants"][name] = {"error": repr(e)[:300]}
     ok = {n: r for n, r in out["variants"].items() if "value" in r}
     if ok:
         best = min(ok, key=lambda n: ok[n]["ms_per_step"])

@@ -6,7 +6,7 @@ Python identifier).  Hot path: hand-written sm_100a CUDA in ``csrc/`` behind the
 """
 from .interface import (FlashAttentionFunction, attention, flash_attention, flash_attention_bshd, tma_compatible, flash_attention_backward, flash_attention_backward_parts,
                         flash_attention_delta, flash_attention_forward, merge_partial_, flash_attention_backward_fused,
-                        set_deterministic, is_deterministic, set_fused128, Ranges, flash_attention_varlen)
+                        set_deterministic, is_deterministic, set_fused128, set_shared_sms, Ranges, flash_attention_varlen)
 from .host_pipeline import HostAttentionPipeline, flash_attention_host
 from .verify import verify_results
 from .flops import attention_flops, tflops
@@ -14,4 +14,4 @@ from .flops import attention_flops, tflops
 __all__ = ["flash_attention", "attention", "flash_attention_bshd", "tma_compatible", "FlashAttentionFunction", "flash_attention_forward",
            "flash_attention_backward", "flash_attention_backward_parts", "flash_attention_delta", "merge_partial_", "verify_results",
            "attention_flops", "tflops", "HostAttentionPipeline", "flash_attention_host", "flash_attention_backward_fused",
-           "set_deterministic", "is_deterministic", "set_fused128", "Ranges", "flash_attention_varlen"]
+           "set_deterministic", "is_deterministic", "set_fused128", "set_shared_sms", "Ranges", "flash_attention_varlen"]

@@ -33,6 +33,7 @@ SYMBOLS = {
     "fa_last_error": (ctypes.c_char_p, []),
     "fa_sm100_version": (_i, []),
     "fa_sm100_launch_count": (ctypes.c_ulonglong, []),
+    "fa_sm100_set_shared_sms": (ctypes.c_int, [ctypes.c_int]),
     "fa_sm100_last_hang": (_i, [ctypes.POINTER(ctypes.c_uint * 4)]),
 }
 

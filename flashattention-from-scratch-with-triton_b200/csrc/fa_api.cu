@@ -20,6 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_shared_sms{0};       // fa_sm100_set_shared_sms: persistent CTAs draw their first item from the counter too
 
 int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -195,6 +196,7 @@ extern "C" {
 int fa_sm100_version(void) { return 100; }
 const char* fa_last_error(void) { return g_err; }
 unsigned long long fa_sm100_launch_count(void) { return g_launches.load(); }
+int fa_sm100_set_shared_sms(int on) { return g_shared_sms.exchange(on ? 1 : 0); }
 
 int fa_sm100_supported(int D, int dtype, int Sq, int Sk) {
     return (D == 64 || D == 128) && (dtype == 0 || dtype == 1) && Sq > 0 && Sk > 0;
@@ -260,6 +262,7 @@ int fa_sm100_fwd_opt(const void* q, const void* k, const void* v, void* o, float
     p.lse = lse;
     p.row_lo = row_lo; p.row_hi = row_hi; p.drop = drop;
     p.sched = dev->sched_ring + sched_slot();           // self-resetting counter pair (sched_retire): no memset on the stream
+    p.dyn_first = g_shared_sms.load(std::memory_order_relaxed);
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = p.n_items < dev->sms ? p.n_items : dev->sms;
     if (D == 64) return dtype ? launch_fwd<64, true>(mq, mk, mv, mo, p, grid, dev->ordinal, st) : launch_fwd<64, false>(mq, mk, mv, mo, p, grid, dev->ordinal, st);
@@ -374,6 +377,7 @@ int fa_sm100_bwd_opt(const void* q, const void* k, const void* v, const void* o,
     {   // two self-resetting counter pairs from the ring
         const unsigned int slot = sched_slot();
         p.sched_dkv = dev->sched_ring + slot; p.sched_dq = dev->sched_ring + slot + 2;
+        p.dyn_first = g_shared_sms.load(std::memory_order_relaxed);
     }
     p.dev = dev->ordinal;
     rc = launch_bwd(mq, mk, mv, mdo, mdq, mdk, mdv, p, D, dtype, parts, st);
@@ -449,6 +453,7 @@ int fa_sm100_bwd_fused_opt(const void* q, const void* k, const void* v, const vo
     p.hc_dq = heads_per_chunk(BH, 4.0 * ((double)Sq + Sk) * D);
     p.hc_dkv = heads_per_chunk(BH / p.G, 4.0 * ((double)p.G * Sq + Sk) * D);
     p.sched_dkv = dev->sched_ring + sched_slot(); p.sched_dq = nullptr;
+    p.dyn_first = g_shared_sms.load(std::memory_order_relaxed);
     p.dev = dev->ordinal;
     if (D == 128)
         rc = dtype ? launch_bwd_fused128_t<true>(mq, mk, mv, mdo, mdk, mdv, macc, p, dq_acc, dq, s_dq, st, parts)

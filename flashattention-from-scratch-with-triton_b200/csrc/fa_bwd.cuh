@@ -37,6 +37,7 @@ struct BwdParams {
     unsigned int* sched_dkv;   // work counters (zeroed before launch) for the persistent kernels
     unsigned int* sched_dq;
     int sms;
+    int dyn_first;             // draw the first item from the counter too (shared SMs, see sched_first)
     int dev;                   // device ordinal of the launch (host side only: per-device kernel attributes)
     int hc_dkv, hc_dq;         // heads per scheduling chunk (item_to_head_tile) for the K/V-tile and the Q-tile kernels
     // Optional range masks (FwdParams): row_lo/row_hi [B, Sq] = keys visible to a query row (used by the dQ kernel);
@@ -353,7 +354,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
             __syncwarp();
             uint32_t git = 0, nacc = 0;
-            int item = blockIdx.x;
+            int item = sched_first(p.sched_dkv, FA_BWD_PERSISTENT ? p.dyn_first : 0);
             for (uint32_t ix = 0;; ++ix) {
                 const uint32_t slot = ix & 1;
                 mbar_wait(&sched_empty[slot], ((ix >> 1) & 1) ^ 1, 441);
@@ -389,8 +390,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     }
                     ++nacc;
                 }
-                if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dkv, 1u) + (int)gridDim.x : n_items;
-                item = __shfl_sync(0xffffffffu, item, 0);
+                item = FA_BWD_PERSISTENT ? sched_next(p.sched_dkv, p.dyn_first) : n_items;
             }
             if (lane_id() == 0) sched_retire(p.sched_dkv);
         }
@@ -727,7 +727,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
         __syncwarp();
         uint32_t g = 0;
-        int item = blockIdx.x;
+        int item = sched_first(p.sched_dq, FA_BWD_PERSISTENT ? p.dyn_first : 0);
         for (uint32_t ix = 0;; ++ix) {
             const uint32_t slot = ix & 1;
             mbar_wait(&sched_empty[slot], ((ix >> 1) & 1) ^ 1, 541);
@@ -759,8 +759,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 #pragma unroll
                 for (int c = 0; c < C::kChunks; ++c) tma_load_4d_e(sVj + c * 16384, &mapV, &v_full[vs], c * 64, (jb + it) * 128, (bh % p.H) / p.G, bh / p.H);
             }
-            if (lane_id() == 0) item = FA_BWD_PERSISTENT ? (int)atomicAdd(p.sched_dq, 1u) + (int)gridDim.x : n_items;
-            item = __shfl_sync(0xffffffffu, item, 0);
+            item = FA_BWD_PERSISTENT ? sched_next(p.sched_dq, p.dyn_first) : n_items;
         }
         if (lane_id() == 0) sched_retire(p.sched_dq);
     } else if (warp == 8) {

@@ -244,7 +244,7 @@ fa_bwd_fused128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
         if (lane_id() == 0) { tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapdO); }
         __syncwarp();
         uint32_t git = 0;
-        int item = blockIdx.x;
+        int item = sched_first(p.sched_dkv, p.dyn_first);
         for (uint32_t ix = 0;; ++ix) {
             const uint32_t slot = ix & 1;
             mbar_wait(&sched_empty[slot], ((ix >> 1) & 1) ^ 1, 741);
@@ -282,8 +282,7 @@ fa_bwd_fused128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
                 #pragma unroll
                 for (int c = 0; c < 2; ++c) tma_load_4d_e(sV + c * 16384, &mapV, v_full, c * 64, jt * 128, bh % p.Hk, bh / p.Hk);
             }
-            if (lane_id() == 0) item = (int)atomicAdd(p.sched_dkv, 1u) + (int)gridDim.x;
-            item = __shfl_sync(0xffffffffu, item, 0);
+            item = sched_next(p.sched_dkv, p.dyn_first);
         }
         if (lane_id() == 0) sched_retire(p.sched_dkv);
     } else if (warp == 8) {

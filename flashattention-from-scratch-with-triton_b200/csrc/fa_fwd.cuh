@@ -31,6 +31,7 @@ struct FwdParams {
     float scale_log2;      // scale * log2(e)
     float* lse;            // [BH, Sq] fp32
     unsigned int* sched;   // work counter, zeroed before launch
+    int dyn_first;         // draw the first item from the counter too (shared SMs, see sched_first)
     // Optional per-row key ranges [B, Sq] (var-len packing, key padding, windows): query row i of batch b sees keys
     // [row_lo, row_hi) (and, if causal, only keys <= i).  Both arrays must be non-decreasing in i.  NULL = [0, Sk).
     const int* row_lo;
@@ -195,7 +196,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             __syncwarp();
             uint32_t kv_cnt = 0;        // K/V tiles produced so far
             uint32_t q_cnt0 = 0, q_cnt1 = 0;
-            int item = blockIdx.x;
+            int item = sched_first(p.sched, p.dyn_first);
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it & 1;
                 mbar_wait(&sched_empty[slot], ((it >> 1) & 1) ^ 1, 100);
@@ -232,8 +233,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     load_kv(&mapV, 0);
                     for (int j = 1; j < n; ++j) { load_kv(&mapK, j); load_kv(&mapV, j); }
                 }
-                if (lane_id() == 0) item = (int)atomicAdd(p.sched, 1u) + (int)gridDim.x;
-                item = __shfl_sync(0xffffffffu, item, 0);
+                item = sched_next(p.sched, p.dyn_first);
             }
             if (lane_id() == 0) sched_retire(p.sched);
         }

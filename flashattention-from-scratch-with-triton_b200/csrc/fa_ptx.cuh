@@ -458,6 +458,25 @@ __device__ __forceinline__ void sched_retire(unsigned int* sched) {
     if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
 }
 
+// First item of a persistent CTA.  Static (item = blockIdx.x, no atomic in front of the first TMA load) when the launch owns the
+// GPU; DRAWN FROM THE COUNTER like every later item when the SMs are shared (dyn != 0: sequence-parallel runs, where NCCL kernels
+// occupy a few SMs while the attention launch starts).  A CTA that cannot be scheduled until an SM frees would otherwise hold its
+// static item — one of the HEAVIEST, the order is heavy-first — hostage until the very end of the launch: measured +15..20 % on
+// every launch that overlapped a transfer (profiles/r02, C5 at 2 GPUs).  Whole warp, converged.
+__device__ __forceinline__ int sched_first(unsigned int* sched, int dyn) {
+    int item = (int)blockIdx.x;
+    if (dyn) {
+        if (lane_id() == 0) item = (int)atomicAdd(sched, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+    }
+    return item;
+}
+__device__ __forceinline__ int sched_next(unsigned int* sched, int dyn) {
+    int item = 0;
+    if (lane_id() == 0) item = (int)atomicAdd(sched, 1u) + (dyn ? 0 : (int)gridDim.x);
+    return __shfl_sync(0xffffffffu, item, 0);
+}
+
 // Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-serialization attribute
 // (launch_pdl) and executes pdl_wait() before its first global-memory access: the launch and the prologue (barrier init, TMEM
 // allocation, tensor-map prefetch) overlap the tail of the previous kernel in the stream; pdl_wait returns once that kernel has

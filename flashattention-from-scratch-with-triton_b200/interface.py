@@ -253,6 +253,12 @@ def set_deterministic(flag: bool) -> bool:
     return prev
 
 
+def set_shared_sms(flag: bool) -> bool:
+    """Tell the kernels that their launches share the GPU with other kernels (NCCL transfers of the sequence-parallel paths):
+    persistent CTAs then draw even their first work item from the counter (include/fa_sm100.h).  Returns the previous setting."""
+    return bool(_cabi.load().fa_sm100_set_shared_sms(int(bool(flag))))
+
+
 def is_deterministic() -> bool:
     return _deterministic
 

@@ -152,6 +152,23 @@ def _parts(B: int, Hk: int, G: int, n: int):
     return [((slice(None), slice(h * G, min(h + per, Hk) * G)), (slice(None), slice(h, min(h + per, Hk)))) for h in range(0, Hk, per)]
 
 
+class _shared_sms:
+    """Context: while a sequence-parallel pass runs with the CUDA kernels, transfers overlap the attention launches."""
+
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        if self.on:
+            from .interface import set_shared_sms
+            self.prev = set_shared_sms(True)
+
+    def __exit__(self, *a):
+        if self.on:
+            from .interface import set_shared_sms
+            set_shared_sms(self.prev)
+
+
 def _mark(timeline, t, name):
     """Optional per-hop timeline: CUDA events on the current stream (GPU tensors only)."""
     if timeline is not None and t.is_cuda:
@@ -170,6 +187,12 @@ def _mark(timeline, t, name):
 
 
 def ring_attention_forward(q, k, v, group=None, ops=None, comm=None, splits=None, timeline=None):
+    """See _ring_attention_forward_impl; with the CUDA kernels the launches are marked as sharing the GPU with the transfers."""
+    with _shared_sms(ops is None and q.is_cuda):
+        return _ring_attention_forward_impl(q, k, v, group, ops, comm, splits, timeline)
+
+
+def _ring_attention_forward_impl(q, k, v, group=None, ops=None, comm=None, splits=None, timeline=None):
     """Causal attention over the global sequence; q,k,v are this rank's zigzag-local [B,H,2c,D] tensors.
     Returns (O [B,H,2c,D] in q.dtype, LSE [B,H,2c] fp32) for the local rows."""
     ops = ops or CudaOps()
@@ -211,6 +234,12 @@ def ring_attention_forward(q, k, v, group=None, ops=None, comm=None, splits=None
 
 
 def ring_attention_backward(q, k, v, O, dO, LSE, group=None, ops=None, comm=None, splits=None, timeline=None):
+    """See _ring_attention_backward_impl; with the CUDA kernels the launches are marked as sharing the GPU with the transfers."""
+    with _shared_sms(ops is None and q.is_cuda):
+        return _ring_attention_backward_impl(q, k, v, O, dO, LSE, group, ops, comm, splits, timeline)
+
+
+def _ring_attention_backward_impl(q, k, v, O, dO, LSE, group=None, ops=None, comm=None, splits=None, timeline=None):
     """Gradients for ring_attention_forward.  Returns (dq, dk, dv) for the local rows, in q.dtype.
 
     Two rings run under the compute: the K/V block of the next hop is prefetched while the current hop's
@@ -366,6 +395,9 @@ class DistCollectives:
         self.dist, self.group = dist, group
         self.world = dist.get_world_size(group); self.rank = dist.get_rank(group)
 
+    def begin(self, phase, arena_need=0):
+        pass
+
     def all_gather(self, t):
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
         if self.world == 1:
@@ -383,6 +415,141 @@ class DistCollectives:
         return recv, None
 
 
+class PeerCollectives:
+    """all_gather / all_to_all over NVLink PEER MEMORY, moved by the COPY ENGINES: no SM is taken from the persistent attention
+    kernels (an NCCL kernel next to a running attention launch costs it 12-16 % — its CTAs cannot co-reside with CTAs that own the
+    whole register file — a copy-engine transfer 3 %; profiles/r02_probe_peer_copy_vs_nccl.json).
+
+    torch symmetric memory provides the peer mappings; the protocol needs no kernel at all:
+      writer  waits (cuStreamWaitValue32 on its own flag words) until every reader has acknowledged the slot's previous use, writes
+              its data into its slot of the symmetric arena, then stores the epoch into the `ready` word it owns on every peer
+              (cuStreamWriteValue32 through the peer mapping) — all on the compute stream, ordered behind the producing kernels;
+      reader  on one of a few side streams: waits for `ready[src] >= epoch` in its OWN memory, copies the peer's slot with
+              cudaMemcpyAsync (device-to-device peer copy = copy engine), then stores the epoch into its `ack` word on the source.
+    Every rank issues the same sequence of collectives, so slots are numbered by call order and `begin(phase)` rewinds the count:
+    the same call site gets the same slot (its own symmetric buffer, and flag index) every step."""
+
+    N_SLOTS = 64
+
+    def __init__(self, group=None, n_streams=4):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from cuda.bindings import driver as drv
+        self.drv = drv
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group); self.rank = dist.get_rank(self.group)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.symm, self.arena, self.hdl, self.peer_arena = symm, {}, {}, {}
+        nflag = 2 * 2 * self.world * self.N_SLOTS                 # [phase][ready | ack][src / dst rank][slot]
+        self.flags = symm.empty(nflag, dtype=torch.int32, device=self.dev)
+        self.flags.zero_()
+        self.fh = symm.rendezvous(self.flags, self.group.group_name)
+        self.peer_flags = [self.fh.get_buffer(r, (nflag,), torch.int32) for r in range(self.world)]
+        torch.cuda.synchronize(); dist.barrier(self.group)
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_streams)]
+        self.epoch = 0; self.phase = None; self.off = 0; self.call = 0
+        self.last_use = {}
+
+    def _flag(self, phase, kind, r, slot):                        # index into the int32 flag array
+        return (((0 if phase == "fwd" else 1) * 2 + kind) * self.world + r) * self.N_SLOTS + slot
+
+    def begin(self, phase, arena_need=0):
+        """Start of a forward / backward pass: rewind the slot counter of that phase."""
+        self.epoch += 1; self.phase = phase; self.call = 0
+
+    def _wait_geq(self, stream, flag_index, value):
+        addr = self.flags.data_ptr() + 4 * flag_index
+        err, = self.drv.cuStreamWaitValue32(stream.cuda_stream, addr, value, self.drv.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_GEQ)
+        assert err == self.drv.CUresult.CUDA_SUCCESS, err
+
+    def _write(self, stream, peer, flag_index, value):
+        addr = self.peer_flags[peer].data_ptr() + 4 * flag_index
+        err, = self.drv.cuStreamWriteValue32(stream.cuda_stream, addr, value, 0)
+        assert err == self.drv.CUresult.CUDA_SUCCESS, err
+
+    def _slot(self, nbytes):
+        """Next slot of the phase: its own symmetric buffer (allocated and exchanged on first use — a collective step, every rank
+        gets here in the same order; one buffer per slot keeps every mapping far below 2 GiB)."""
+        ph = self.phase
+        assert ph is not None, "PeerCollectives.begin(phase) first"
+        slot = self.call; self.call += 1
+        assert slot < self.N_SLOTS
+        key = (ph, slot)
+        if key not in self.arena or self.arena[key].numel() < nbytes:
+            torch.cuda.synchronize()                                         # nobody may still read a buffer that is replaced
+            t = self.symm.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            h = self.symm.rendezvous(t, self.group.group_name)
+            self.arena[key], self.hdl[key] = t, h
+            self.peer_arena[key] = [h.get_buffer(r, (nbytes,), torch.uint8) for r in range(self.world)]
+        return ph, slot, 0
+
+    def _publish(self, ph, slot, fill):
+        """Writer side: wait for the acks of the slot's previous use, fill the slot, raise `ready` on every peer."""
+        cur = torch.cuda.current_stream()
+        prev = self.last_use.get((ph, slot), 0)
+        if prev:
+            for r in range(self.world):
+                if r != self.rank:
+                    self._wait_geq(cur, self._flag(ph, 1, r, slot), prev)
+        fill()
+        for r in range(self.world):
+            if r != self.rank:
+                self._write(cur, r, self._flag(ph, 0, self.rank, slot), self.epoch)
+        self.last_use[(ph, slot)] = self.epoch
+
+    def _pull(self, ph, slot, jobs):
+        """Reader side: jobs = [(src rank, dst tensor, byte offset in the peer arena, nbytes)], spread over the side streams."""
+        cur = torch.cuda.current_stream()
+        ev0 = torch.cuda.Event(); ev0.record(cur)
+        used = []
+        for i, (r, dst, off, nbytes) in enumerate(jobs):
+            st = self.streams[i % len(self.streams)]
+            st.wait_event(ev0)
+            self._wait_geq(st, self._flag(ph, 0, r, slot), self.epoch)
+            with torch.cuda.stream(st):
+                dst.view(torch.uint8).view(-1).copy_(self.peer_arena[(ph, slot)][r][off:off + nbytes], non_blocking=True)
+            self._write(st, r, self._flag(ph, 1, self.rank, slot), self.epoch)
+            if st not in used:
+                used.append(st)
+        evs = []
+        for st in used:
+            e = torch.cuda.Event(); e.record(st); evs.append(e)
+        return _EventWait(evs)
+
+    def all_gather(self, t):
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        ph, slot, off = self._slot(nbytes)
+        mine = self.arena[(ph, slot)][off:off + nbytes]
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self._publish(ph, slot, lambda: mine.copy_(t.view(torch.uint8).view(-1)))
+        out[self.rank].copy_(t)
+        jobs = [((self.rank + i) % self.world, None, off, nbytes) for i in range(1, self.world)]
+        return out, self._pull(ph, slot, [(r, out[r], o, n) for r, _, o, n in jobs])
+
+    def all_to_all(self, send):
+        """send [P, ...]: block p goes to rank p.  (The producer's copy into the arena is the only extra pass.)"""
+        send = send.contiguous()
+        blk = send[0].numel() * send.element_size()
+        ph, slot, off = self._slot(blk * self.world)
+        mine = self.arena[(ph, slot)][off:off + blk * self.world]
+        recv = torch.empty_like(send)
+        self._publish(ph, slot, lambda: mine.copy_(send.view(torch.uint8).view(-1)))
+        recv[self.rank].copy_(send[self.rank])
+        jobs = [((self.rank + i) % self.world, None) for i in range(1, self.world)]
+        return recv, self._pull(ph, slot, [(r, recv[r], off + blk * self.rank, blk) for r, _ in jobs])
+
+
+class _EventWait:
+    def __init__(self, events):
+        self.events = events
+
+    def wait(self):
+        cur = torch.cuda.current_stream()
+        for e in self.events:
+            cur.wait_event(e)
+
+
 def _gloo_all_to_all(dist, outs, ins, group):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     ops = []
@@ -395,12 +562,49 @@ def _gloo_all_to_all(dist, outs, ins, group):
         w.wait()
 
 
-def _head_groups(Hk: int, G: int, n: int):
-    n = max(1, min(n, Hk)); per = -(-Hk // n)
-    return [(slice(h * G, min(h + per, Hk) * G), slice(h, min(h + per, Hk))) for h in range(0, Hk, per)]
+def _head_groups(Hk: int, G: int, n):
+    """(query-head slice, K/V-head slice) per group.  `n` = number of equal groups, or a list of K/V heads per group."""
+    if isinstance(n, int):
+        n = max(1, min(n, Hk)); per = -(-Hk // n)
+        sizes = [min(per, Hk - h) for h in range(0, Hk, per)]
+    else:
+        sizes = [int(x) for x in n if int(x) > 0]
+        assert sum(sizes) == Hk, f"head groups {sizes} do not add up to {Hk} K/V heads"
+    out, h = [], 0
+    for sz in sizes:
+        out.append((slice(h * G, (h + sz) * G), slice(h, h + sz))); h += sz
+    return out
 
 
-def gather_attention_forward(q, k, v, group=None, ops=None, coll=None, groups=4, timeline=None):
+def default_head_groups(Hk: int):
+    """Small group first, then big ones: the first group's all-gather is the only exposed one in the forward, and the backward
+    walks the groups in REVERSE order so that the only exposed all-to-all (the last) is the small group's.  32 heads -> [2, 6, 8, 8, 8]."""
+    if Hk < 8:
+        return [1] * Hk if Hk <= 2 else [1, Hk - 1]
+    a = max(1, Hk // 16); b = max(1, 3 * Hk // 16); rest = Hk - a - b
+    q = rest // 3
+    return [a, b, q, q, rest - 2 * q]
+
+
+def make_cp_group(max_ctas: int = 8, ranks=None):
+    """A dedicated NCCL communicator for the sequence-parallel collectives whose kernels are capped at `max_ctas` CTAs: the
+    attention kernels are persistent (one CTA per SM, whole register file), so every SM an NCCL kernel occupies is an SM the
+    running attention launch does not get; the transfers are small next to the compute they hide under."""
+    import torch.distributed as dist
+    if dist.get_backend() != "nccl":
+        return dist.new_group(ranks=ranks)
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(max_ctas); opts.config.min_ctas = 1
+    return dist.new_group(ranks=ranks, pg_options=opts)
+
+
+def gather_attention_forward(q, k, v, group=None, ops=None, coll=None, groups=None, timeline=None):
+    """See _gather_attention_forward_impl; with the CUDA kernels the launches are marked as sharing the GPU with the transfers."""
+    with _shared_sms(ops is None and q.is_cuda):
+        return _gather_attention_forward_impl(q, k, v, group, ops, coll, groups, timeline)
+
+
+def _gather_attention_forward_impl(q, k, v, group=None, ops=None, coll=None, groups=None, timeline=None):
     """Causal attention over the global sequence; q, k, v are this rank's zigzag-local [B,H,2c,D] / [B,Hk,2c,D] tensors.
     Returns (O, LSE, saved) where `saved` carries the gathered K/V (global order, per head group) and the Ranges for the backward."""
     ops = ops or GatherOps()
@@ -410,7 +614,8 @@ def gather_attention_forward(q, k, v, group=None, ops=None, coll=None, groups=4,
     Hk = k.shape[1]; G = H // Hk
     c = S2 // 2
     ranges = zigzag_ranges(rank, P, c, B, q.device)
-    hg = _head_groups(Hk, G, groups)
+    hg = _head_groups(Hk, G, groups if groups is not None else default_head_groups(Hk))
+    coll.begin("fwd", (k.numel() + v.numel()) * k.element_size() + 512 * len(hg))
     _mark(timeline, q, "fwd:start")
     pend = [(coll.all_gather(k[:, ks].contiguous()), coll.all_gather(v[:, ks].contiguous())) for _, ks in hg]   # all posted up front
     O = torch.empty_like(q); LSE = torch.empty(B, H, S2, dtype=torch.float32, device=q.device)
@@ -430,6 +635,12 @@ def gather_attention_forward(q, k, v, group=None, ops=None, coll=None, groups=4,
 
 
 def gather_attention_backward(q, O, dO, LSE, saved, group=None, ops=None, coll=None, timeline=None):
+    """See _gather_attention_backward_impl; with the CUDA kernels the launches are marked as sharing the GPU with the transfers."""
+    with _shared_sms(ops is None and q.is_cuda):
+        return _gather_attention_backward_impl(q, O, dO, LSE, saved, group, ops, coll, timeline)
+
+
+def _gather_attention_backward_impl(q, O, dO, LSE, saved, group=None, ops=None, coll=None, timeline=None):
     """Gradients for gather_attention_forward.  dQ is local; the dK / dV partials of every key (16-bit, global order) are sent to
     the key's owner (one all-to-all per head group, posted as soon as the group's kernels are enqueued) and summed there in fp32."""
     ops = ops or GatherOps()
@@ -440,27 +651,36 @@ def gather_attention_backward(q, O, dO, LSE, saved, group=None, ops=None, coll=N
     Hk = sum(ks.stop - ks.start for _, ks in hg)
     B, H, S2, D = q.shape
     dk = torch.empty(B, Hk, S2, D, dtype=q.dtype, device=q.device); dv = torch.empty_like(dk)
+    coll.begin("bwd", 2 * P * dk.numel() * dk.element_size() + 512 * len(hg))
     _mark(timeline, q, "bwd:start")
-    pend = []
-    for gi, (qs, ks) in enumerate(hg):
-        Kg, Vg = kv_glob[gi]
-        dqg, dKg, dVg = ops.bwd(q[:, qs], Kg, Vg, O[:, qs], dO[:, qs], LSE[:, qs], ranges)
-        dq[:, qs] = dqg
-        pend.append((coll.all_to_all(_from_global(dKg, P)), coll.all_to_all(_from_global(dVg, P))))
-        _mark(timeline, q, f"bwd:group{gi}")
-    for gi, (qs, ks) in enumerate(hg):
-        (kb, kw), (vb, vw) = pend[gi]
+    pend = {}
+    order = list(range(len(hg)))[::-1]                        # reverse: the last (exposed) all-to-all belongs to the smallest group
+
+    def finish(gi):                                           # partials of group gi have arrived: sum them in fp32, round once
+        (kb, kw), (vb, vw) = pend.pop(gi)
         for w in (kw, vw):
             if w is not None:
                 w.wait()
-        dk[:, ks] = kb.float().sum(0).to(q.dtype); dv[:, ks] = vb.float().sum(0).to(q.dtype)
+        ks = hg[gi][1]
+        dk[:, ks] = torch.sum(kb, dim=0, dtype=torch.float32).to(q.dtype); dv[:, ks] = torch.sum(vb, dim=0, dtype=torch.float32).to(q.dtype)
+
+    for n, gi in enumerate(order):
+        qs, ks = hg[gi]
+        Kg, Vg = kv_glob[gi]
+        dqg, dKg, dVg = ops.bwd(q[:, qs], Kg, Vg, O[:, qs], dO[:, qs], LSE[:, qs], ranges)
+        dq[:, qs] = dqg
+        pend[gi] = (coll.all_to_all(_from_global(dKg, P)), coll.all_to_all(_from_global(dVg, P)))
+        if n >= 1:
+            finish(order[n - 1])                              # the previous group's transfer ran under this group's kernels
+        _mark(timeline, q, f"bwd:group{gi}")
+    finish(order[-1])
     _mark(timeline, q, "bwd:end")
     return dq, dk, dv
 
 
 class GatherFlashAttentionFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, group=None, coll=None, groups=4, timeline=None):
+    def forward(ctx, q, k, v, group=None, coll=None, groups=None, timeline=None):
         assert q.dtype in (torch.float16, torch.bfloat16) and q.ndim == 4
         q_ = q.contiguous()
         O, LSE, saved = gather_attention_forward(q_, k, v, group, None, coll, groups, timeline)
@@ -476,7 +696,7 @@ class GatherFlashAttentionFunction(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None
 
 
-def gather_flash_attention(q, k, v, group=None, coll=None, groups=4, timeline=None):
+def gather_flash_attention(q, k, v, group=None, coll=None, groups=None, timeline=None):
     """Causal attention over a zigzag-sharded sequence, NVSwitch variant (see the section comment): same inputs / outputs as
     ring_flash_attention."""
     return GatherFlashAttentionFunction.apply(q, k, v, group, coll, groups, timeline)
@@ -522,6 +742,9 @@ class ThreadCollectives:
         import threading
         shared = dict(barrier=threading.Barrier(world, timeout=120), slots=[None] * world)
         return [ThreadCollectives(r, world, shared) for r in range(world)]
+
+    def begin(self, phase, arena_need=0):
+        pass
 
     def _exchange(self, t, pick):
         sh_ = self.shared

@@ -170,6 +170,13 @@ int fa_sm100_version(void);
 /* Number of this library's kernels launched by the calling process so far (bench bookkeeping). */
 unsigned long long fa_sm100_launch_count(void);
 
+/* Process-wide switch for launches that SHARE the GPU with other kernels (sequence-parallel runs: NCCL transfers overlap the
+ * attention launches).  The attention kernels are persistent, one CTA per SM; by default CTA i starts on item i without touching
+ * the work counter.  With on != 0 the first item is drawn from the counter like every later one, so a CTA that is scheduled late
+ * (its SM was busy) takes whatever is left instead of holding one of the heaviest items until the end of the launch.
+ * Returns the previous setting.  Results are identical either way. */
+int fa_sm100_set_shared_sms(int on);
+
 /* Debug: if a kernel aborted on a pipeline time-out, copies {tag, block, thread, parity} of the
  * first waiter that gave up into out[4] and returns 1; returns 0 if no time-out was recorded. */
 int fa_sm100_last_hang(unsigned int out[4]);

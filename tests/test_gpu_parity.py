@@ -334,6 +334,32 @@ def test_fused_backward_matches_two_kernel_backward():
             assert _close(fused[1].cpu(), rdK) and _close(fused[2].cpu(), rdV)
 
 
+def test_shared_sm_mode_is_bitwise_identical():
+    """fa_sm100_set_shared_sms(1): persistent CTAs draw even their first item from the work counter (for launches that overlap
+    NCCL transfers).  Which CTA computes which tile never changes a result: forward and the two-kernel backward are bitwise equal
+    in both modes, at D = 64 and 128, also when the grid is larger than the number of items."""
+    from flashattn_b200 import interface as I
+    for (B, H, S, D, causal) in ((1, 2, 256, 64, True), (2, 8, 1024, 128, True), (4, 16, 2048, 64, False), (1, 1, 128, 128, False)):
+        Q, K, V, dO = (t.cuda() for t in orc.make_inputs(B, H, S, S, D, torch.bfloat16, seed=B + S))
+        prev_det = fa.set_deterministic(True)
+        try:
+            outs = []
+            for mode in (False, True, False):
+                prev = I.set_shared_sms(mode)
+                try:
+                    O, LSE = fa.flash_attention_forward(Q, K, V, causal)
+                    outs.append((O, LSE) + tuple(fa.flash_attention_backward(Q, K, V, O, dO, LSE, causal)))
+                finally:
+                    I.set_shared_sms(prev)
+            for a, b in zip(outs[0], outs[1]):
+                assert torch.equal(a, b)
+            for a, b in zip(outs[0], outs[2]):      # and the counters were left clean for the next launch
+                assert torch.equal(a, b)
+        finally:
+            fa.set_deterministic(prev_det)
+    assert not I.set_shared_sms(False)
+
+
 def test_first_call_on_a_thread_without_cuda_context():
     """cuTensorMapEncodeTiled is a driver call and needs a current context; a thread that has made no CUDA runtime call yet (the
     autograd worker running the first backward of a process, with every output coming from the caching allocator) has none.  The

@@ -50,6 +50,24 @@ def _worker(rank, world, port, ret):
             d = (x.detach().cpu().float() - r).abs()
             errs[name] = float((d / (1e-2 + 1e-2 * r.abs())).max())
         out["ring_norm_err"] = errs
+        # the one-shot kernel on the whole sequence, same inputs: the yardstick for the sharded variants' error
+        qf, kf, vf = (t.cuda().requires_grad_(True) for t in (Q, K, V))
+        Of = fa.flash_attention(qf, kf, vf, True); Of.backward(dO.cuda())
+        out["one_shot_norm_err"] = {n: float(((x.detach().cpu().float() - r).abs() / (1e-2 + 1e-2 * r.abs())).max())
+                                    for n, x, r in (("O", Of, rO), ("dQ", qf.grad, rdQ), ("dK", kf.grad, rdK), ("dV", vf.grad, rdV))}
+        # ---- NVSwitch variant (gather): NCCL collectives, then peer memory + copy engines; two steps each (slot reuse, acks)
+        for name, coll in (("gather_nccl", None), ("gather_peer", sh.PeerCollectives())):
+            for step in range(2):
+                q.grad = None; k.grad = None; v.grad = None
+                O = sh.gather_flash_attention(q, k, v, None, coll, [1, 1])
+                O.backward(do)
+            torch.cuda.synchronize()
+            errs = {}
+            for tn, x, r in (("O", O, rO), ("dQ", q.grad, rdQ), ("dK", k.grad, rdK), ("dV", v.grad, rdV)):
+                r = sh.zigzag_split(r, rank, world)
+                d = (x.detach().cpu().float() - r).abs()
+                errs[tn] = float((d / (1e-2 + 1e-2 * r.abs())).max())
+            out[name + "_norm_err"] = errs
         ret[rank] = out
     finally:
         dist.destroy_process_group()
@@ -63,7 +81,10 @@ def test_sharding_and_ring_on_gpus():
         mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
         for r in range(world):
             assert ret[r]["shard_bitwise"], r
-            assert max(ret[r]["ring_norm_err"].values()) < 1.5, (r, ret[r])
+            # sharded results: inside the contract (atol = rtol = 1e-2) or no worse than 1.1 x the one-shot kernel on the same inputs
+            bound = max(1.0, 1.1 * max(ret[r]["one_shot_norm_err"].values()))
+            for variant in ("ring", "gather_nccl", "gather_peer"):
+                assert max(ret[r][variant + "_norm_err"].values()) <= bound, (r, variant, ret[r])
 
 
 def test_second_device_in_the_same_process():
