@@ -229,8 +229,11 @@ def main():
     ap.add_argument("--dtype", default=None, choices=[None, "bf16", "fp16"])
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / also / e2e / ring / kernels (profiling runs)")
     ap.add_argument("--no-ring", action="store_true")
+    ap.add_argument("--ring-child", default=None, metavar="FILE", help="internal: run only the C5 block and write its JSON to FILE")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    if a.ring_child:
+        return ring_child(a)
 
     # libraries (NCCL's version banner, Triton autotune chatter) may print to fd 1: keep stdout for the ONE JSON line
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -444,11 +447,30 @@ def main():
         line["also"] = {wl: also_workload(wl) for wl in ("C2", "C3") if wl != a.workload}
 
     # ------------------------------- ring: C5 over N >= 2 GPUs -------------------------------
+    # Runs in CHILD processes (one per rank, their own rendezvous on MASTER_PORT + 17): a CUDA fault in one of the transport variants
+    # is sticky and would take the process — and the headline line — with it; the children write what they have measured after
+    # every variant, so a failure costs only the variants after it.
     if dist_on and a.impl == "ours" and not a.no_extras and not a.no_ring:
+        import tempfile
+        ring_file = os.path.join(tempfile.gettempdir(), f"fa_bench_ring_{os.environ.get('MASTER_PORT', '0')}.json")
+        if rank == 0 and os.path.exists(ring_file):
+            os.remove(ring_file)
+        barrier()
+        env = dict(os.environ, MASTER_PORT=str(int(os.environ.get("MASTER_PORT", "29500")) + 17), TORCHELASTIC_USE_AGENT_STORE="False")
         try:
-            line["ring"] = ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks)
-        except Exception as e:      # the headline line must survive a ring failure; the failure itself is reported
-            line["ring"] = {"error": repr(e)[:400]}
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--ring-child", ring_file, "--dtype", dtype_name],
+                                env=env, stdout=subprocess.DEVNULL, stderr=sys.stderr, timeout=150)
+            rc = cp.returncode
+        except subprocess.TimeoutExpired:
+            rc = "timeout after 150 s"
+        barrier()
+        if rank == 0:
+            try:
+                line["ring"] = json.load(open(ring_file))
+            except Exception as e:
+                line["ring"] = {"error": f"no result from the ring child processes ({e!r})"}
+            if rc != 0:
+                line["ring"]["child_exit"] = rc
 
     if rank == 0 and not a.no_extras:
         if a.impl == "ours":
@@ -476,7 +498,41 @@ def main():
     return 0
 
 
-def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks, steps=3):
+def ring_child(a):
+    """The C5 block in its own process group (see main): rank 0 rewrites FILE after every variant."""
+    os.dup2(2, 1)
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    import datetime
+    # its own TCP store on MASTER_PORT (the parent passed MASTER_PORT + 17): under torchrun the env:// rendezvous would look for the
+    # elastic agent's store, which lives on the parent's port
+    dist.init_process_group("nccl", init_method=f"tcp://{os.environ.get('MASTER_ADDR', '127.0.0.1')}:{os.environ['MASTER_PORT']}",
+                            rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=120))
+    import flashattn_b200 as fa
+
+    def barrier():
+        dist.barrier(); torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def save(out):
+        if rank == 0:
+            tmp = a.ring_child + ".tmp"
+            json.dump(out, open(tmp, "w")); os.replace(tmp, a.ring_child)
+
+    dtype = torch.bfloat16 if (a.dtype or "bf16") == "bf16" else torch.float16
+    ring_block(fa, dist, dev, rank, world, dtype, _peaks(), barrier, max_over_ranks, save=save)
+    barrier()
+    dist.destroy_process_group()
+    return 0
+
+
+def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks, steps=3, save=None):
     """BASELINE config C5 (B=1 H=32 N=131072 D=128 bf16 causal) sequence-sharded (zigzag) over the ranks, both variants of
     flashattn_b200.sharding, timed like the headline (CUDA events per step, max over ranks):
       ring    K/V blocks and the fp32 dK/dV accumulators travel neighbour to neighbour over NCCL send/recv, P hops
@@ -493,13 +549,17 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
     q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
     flops = 3.5 * 4 * B * H * N * N * D / 2
 
+    def note(msg):                                         # progress on stderr (stdout carries the one JSON line)
+        print(f"[ring_block rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     def run(fn):
         def step(timeline=None):
             O = fn(q, k, v, timeline)
             O.backward(do)
             q.grad = None; k.grad = None; v.grad = None
-        step(); step()                                            # communicator set-up and allocator warm-up
-        barrier()
+        step(); torch.cuda.synchronize(); note("first step done")
+        step()                                                    # communicator set-up and allocator warm-up
+        barrier(); note("warm-up done")
         ts = []
         for _ in range(steps):
             s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
@@ -507,7 +567,7 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
             ts.append(s.elapsed_time(e))
         ms = max_over_ranks(sum(ts) / len(ts))
         tl = []
-        barrier(); step(tl); torch.cuda.synchronize()
+        barrier(); step(tl); torch.cuda.synchronize(); note(f"timed: {ms:.2f} ms")
         val = flops / (ms * 1e-3) / 1e12
         return dict(ms_per_step=ms, value=val, unit="TFLOPS", per_gpu_tflops=val / world,
                     per_gpu_frac_of_measured_peak=val / world / peak["bf16_burst"],
@@ -515,7 +575,18 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
 
     out = dict(workload=f"C5: B={B} H={H} N={N} D={D} causal fwd+bwd, zigzag sequence sharding over {world} GPUs (N/{world} = {S2} rows per rank)",
                variants={})
+
+    def summary():
+        ok = {n: r for n, r in out["variants"].items() if "value" in r}
+        res = dict(out)
+        if ok:
+            best = min(ok, key=lambda n: ok[n]["ms_per_step"])
+            res.update(variant=best, **{k_: ok[best][k_] for k_ in ("ms_per_step", "value", "unit", "per_gpu_tflops", "per_gpu_frac_of_measured_peak",
+                                                                  "per_gpu_frac_of_measured_sustained_peak")})
+        return res
+
     try:
+        note("variant ring")
         r, tl = run(lambda q_, k_, v_, t: sh.ring_flash_attention(q_, k_, v_, None, None, None, t))
         ev = dict(tl); hops = []
         for ph in ("fwd", "bwd"):
@@ -530,11 +601,17 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
     except Exception as e:
         out["variants"]["ring"] = {"error": repr(e)[:300]}
     max_ctas = int(os.environ.get("FA_CP_NCCL_MAX_CTAS", "8"))
-    # the peer-memory variant runs last: creating another NCCL communicator (make_cp_group) AFTER symmetric-memory buffers were
-    # exchanged on the default group ended in a launch failure on this stack (torch 2.11 / NCCL 2.28); the other order is fine
-    for name, grp in (("gather", "capped"), ("gather_default_nccl_ctas", None), ("gather_peer", "peer")):
+    kinds = {"gather": None, "gather_capped_nccl_ctas": "capped", "gather_peer": "peer"}
+    wanted = [v for v in os.environ.get("FA_BENCH_CP_VARIANTS", "gather,gather_peer").split(",") if v in kinds]
+    # (the peer-memory variant runs last: creating another NCCL communicator AFTER symmetric-memory buffers were exchanged on the
+    # default group ended in a launch failure on this stack — torch 2.11 / NCCL 2.28)
+    for name in sorted(wanted, key=lambda n: n == "gather_peer"):
+        grp = kinds[name]
+        if save:
+            save(summary())
         torch.cuda.empty_cache()
         try:
+            note(f"variant {name}")
             group = sh.make_cp_group(max_ctas) if grp == "capped" else None
             coll = sh.PeerCollectives() if grp == "peer" else None
             r, tl = run(lambda q_, k_, v_, t: sh.gather_flash_attention(q_, k_, v_, group, coll, None, t))
@@ -550,12 +627,9 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
             out["variants"][name] = r
         except Exception as e:
             out["variants"][name] = {"error": repr(e)[:300]}
-    ok = {n: r for n, r in out["variants"].items() if "value" in r}
-    if ok:
-        best = min(ok, key=lambda n: ok[n]["ms_per_step"])
-        out.update(variant=best, **{k_: ok[best][k_] for k_ in ("ms_per_step", "value", "unit", "per_gpu_tflops", "per_gpu_frac_of_measured_peak",
-                                                              "per_gpu_frac_of_measured_sustained_peak")})
-    return out
+    if save:
+        save(summary())
+    return summary()
 
 
 if __name__ == "__main__":

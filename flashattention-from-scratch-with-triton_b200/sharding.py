@@ -156,7 +156,8 @@ class _shared_sms:
     """Context: while a sequence-parallel pass runs with the CUDA kernels, transfers overlap the attention launches."""
 
     def __init__(self, on):
-        self.on = on
+        import os
+        self.on = on and os.environ.get("FA_CP_SHARED_SMS", "0") not in ("", "0")      # opt-in: no gain measured so far
 
     def __enter__(self):
         if self.on:

@@ -123,13 +123,15 @@ int fa_sm100_bwd_opt(const void* q, const void* k, const void* v, const void* o,
                      int B, int H, int Hk, int Sq, int Sk, int D, int dtype, int causal, float sm_scale,
                      const long long* strides, const fa_sm100_options* opt, void* stream, int parts);
 
-/* Fused single-pass backward, head dim 64 only: one kernel computes dK, dV and dQ with 5 GEMMs per
+/* Fused single-pass backward (head dim 64: csrc/fa_bwd_fused.cuh, head dim 128: csrc/fa_bwd_fused128.cuh — the plain
+ * operator only there, no range masks / dropout): one kernel computes dK, dV and dQ with 5 GEMMs per
  * (kv tile, q tile) pair and one exponential per score element, instead of the dQ + dK/dV kernel pair above
  * (reference launcher code/My_FlashAttention_optimized.py:111-126: 7 GEMMs, two exponentials).  dQ partials are summed over kv
  * tiles in an fp32 workspace `dq_acc` ([B,H,Sq,D] contiguous fp32, fa_sm100_bwd_fused_workspace() bytes, owned by the caller,
  * need not be initialised) by TMA reduce-add, then scaled and converted into `dq`.  Runs delta -> fused kernel -> convert.
  * dK/dV are bitwise reproducible; dQ's fp32 summation order over kv tiles depends on scheduling (use fa_sm100_bwd_strided
- * for the deterministic path).  Arguments otherwise as fa_sm100_bwd_strided; D != 64 returns FA_ERR_HEADDIM.
+ * for the deterministic path).  Arguments otherwise as fa_sm100_bwd_strided.  The Python operator uses it by default at D = 64
+ * (1.4x the two-kernel backward there) and on request at D = 128 (measured at parity with the two-kernel backward).
  * parts: 0 = everything, else a mask of FA_BWD_DELTA (delta + zeroing of dq_acc), FA_BWD_FUSED, FA_BWD_CONVERT (per-kernel timing). */
 #define FA_BWD_FUSED 8
 #define FA_BWD_CONVERT 16
