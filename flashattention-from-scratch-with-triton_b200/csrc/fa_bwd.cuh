@@ -608,10 +608,13 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             gi += n_it;
             // ---- epilogue: dV, dK*scale -> 16-bit -> smem staging -> TMA store
             mbar_wait(acc_full, ix & 1, 433); tc_fence_after();
-            if (C::kSepStage) {                              // the previous item's store must have read the staging
-                if (tid == 0 && store_pending) tma_store_wait_read0();
-                named_bar_sync(1, 256);
-            }
+            // The previous item's store must have read the staging before anybody overwrites it.  tid 0 has waited for that read
+            // (here when the staging is separate, right behind its store when it aliases K/V); the barrier puts EVERY thread behind
+            // it.  Without it (round 1, aliased staging) an item with n_it == 0 — whose accumulators are "complete" at once —
+            // let the other threads zero the staging while the previous item's dK/dV store was still reading it: the tile in
+            // front of an empty item came out partly zero, run-to-run different (found by the C5 stress run, r02).
+            if (C::kSepStage && tid == 0 && store_pending) tma_store_wait_read0();
+            named_bar_sync(1, 256);
             stage_grad_half<D, kBf16>(tmem + lane_field + kColDV, sOutV, r, h, 1.0f, n_it == 0);
             stage_grad_half<D, kBf16>(tmem + lane_field + kColDK, sOutK, r, h, p.scale, n_it == 0);
             tc_fence_before();
@@ -907,10 +910,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             gi += n_it;
             // ---- epilogue: dQ*scale -> 16-bit -> smem staging -> TMA store
             mbar_wait(acc_full, ix & 1, 532); tc_fence_after();
-            if (C::kSepStage) {                              // the previous item's store must have read the staging
-                if (tid == 0 && store_pending) tma_store_wait_read0();
-                named_bar_sync(1, 256);
-            }
+            // as in the dK/dV kernel: every thread behind tid 0's wait for the previous store's read of the staging (an item with
+            // n_it == 0 reaches this point immediately)
+            if (C::kSepStage && tid == 0 && store_pending) tma_store_wait_read0();
+            named_bar_sync(1, 256);
             stage_grad_half<D, kBf16>(tmem + lane_field + kColDQ, sOut, r, h, p.scale, n_it == 0);
             tc_fence_before();
             mbar_arrive(acc_empty);                          // dQ drained from TMEM
