@@ -240,7 +240,8 @@ def flash_attention_backward_parts(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_ca
 # Backward algorithm.  Head dim 64 defaults to the fused single-pass kernel (5 GEMMs and one exponential per score
 # element; dQ summed over kv tiles by TMA reduce-add in fp32, so its low-order bits depend on scheduling — like
 # PyTorch's own flash backward).  set_deterministic(True) or FA_SM100_DETERMINISTIC=1 selects the reference's
-# atomic-free two-kernel structure (code/My_FlashAttention_optimized.py:111-126) everywhere; head dim 128 always uses it.
+# atomic-free two-kernel structure (code/My_FlashAttention_optimized.py:111-126) everywhere; head dim 128 uses it unless
+# set_fused128(True) / FA_SM100_FUSED128=1 (measured at parity there).
 _deterministic = os.environ.get("FA_SM100_DETERMINISTIC", "0") not in ("", "0")
 
 
@@ -286,7 +287,8 @@ BWD_FUSED, BWD_CONVERT = 8, 16
 
 def flash_attention_backward_fused(Q, K, V, O, dO, LSE, dQ, dK, dV, delta, is_causal, sm_scale=None, dq_acc=None, parts=0,
                                    ranges=None, dropout_p=0.0, dropout_seed=0):
-    """delta -> fused dK/dV/dQ kernel -> dQ conversion (head dim 64).  dq_acc: optional fp32 [B,H,S_q,D] workspace."""
+    """delta -> fused dK/dV/dQ kernel -> dQ conversion (head dim 64, or 128 for the plain operator: no ranges / dropout there).
+    dq_acc: optional fp32 [B,H,S_q,D] workspace."""
     lib = _cabi.load()
     B, H, S_q, D = Q.shape
     S_k = K.shape[2]

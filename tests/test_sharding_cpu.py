@@ -281,3 +281,31 @@ def test_range_mask_tile_ranges_cover_every_visible_pair(causal):
                 qs = torch.nonzero(vis[:, jt * 128:jt * 128 + 128].any(1)).flatten()
                 if qs.numel():
                     assert i_start * 128 <= int(qs.min()) and int(qs.max()) < i_end * 128, (jt, i_start, i_end)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_zigzag_ranges_and_head_groups(world):
+    """Host logic of the gather variant: the Ranges of every rank describe ONE mask from both sides (validate()), together they cover
+    the causal mask exactly once, and the head groups partition the K/V heads in order."""
+    c = 5
+    N = 2 * c * world
+    seen = torch.zeros(N, N, dtype=torch.int32)
+    for rank in range(world):
+        r = sh.zigzag_ranges(rank, world, c, 2, "cpu").validate()
+        a, b = sh.zigzag_chunks(rank, world)
+        gpos = torch.cat([a * c + torch.arange(c), b * c + torch.arange(c)])
+        j = torch.arange(N)
+        vis = (j[None, :] >= r.row_lo[0][:, None]) & (j[None, :] < r.row_hi[0][:, None])          # [2c, N]
+        seen[gpos] += vis.int()
+    causal = (torch.arange(N)[:, None] >= torch.arange(N)[None, :]).int()
+    assert torch.equal(seen, causal)
+    for Hk in (1, 2, 3, 8, 16, 32, 40):
+        sizes = sh.default_head_groups(Hk)
+        assert sum(sizes) == Hk and all(s > 0 for s in sizes) and sizes[0] == min(sizes)
+        for G in (1, 4):
+            hg = sh._head_groups(Hk, G, sizes)
+            assert [ks.stop - ks.start for _, ks in hg] == sizes and hg[0][1].start == 0 and hg[-1][1].stop == Hk
+            assert all(qs.start == ks.start * G and qs.stop == ks.stop * G for qs, ks in hg)
+    assert [ks.stop - ks.start for _, ks in sh._head_groups(10, 1, 4)] == [3, 3, 3, 1]
+    t = torch.arange(world * 2 * 3 * 2 * c * 4, dtype=torch.float32).view(world, 2, 3, 2 * c, 4)
+    assert torch.equal(sh._from_global(sh._to_global(t), world), t)
