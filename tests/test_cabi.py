@@ -102,3 +102,26 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path, lib):
+    """include/fa_sm100.h is the drop-in boundary for ANY host language: it must compile as C99 (no C++, no torch types) and a C
+    program linked against libfa_sm100.so must resolve every entry point it declares (called here only for argument validation
+    and the capability query: no GPU needed)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "flashattention-from-scratch-with-triton_b200")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include <stdio.h>\n#include "fa_sm100.h"\n'
+                   "int main(void) {\n"
+                   "  int rc = fa_sm100_fwd(0, 0, 0, 0, 0, 1, 2, 128, 128, 64, 1, 0, 0.0f, 0);   /* null tensors: validation only */\n"
+                   '  printf("%d %d %d %s\\n", fa_sm100_version(), fa_sm100_supported(128, 1, 77, 300), rc, fa_last_error());\n'
+                   "  return 0;\n}\n")
+    exe = tmp_path / "use_header"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L" + pkg, "-l:libfa_sm100.so", "-Wl,-rpath," + pkg], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split(maxsplit=3)
+    assert int(out[0]) >= 100 and int(out[1]) == 1 and int(out[2]) == -1 and "null" in out[3]
