@@ -602,10 +602,10 @@ def ring_block(fa, dist, dev, rank, world, dtype, peak, barrier, max_over_ranks,
         out["variants"]["ring"] = {"error": repr(e)[:300]}
     max_ctas = int(os.environ.get("FA_CP_NCCL_MAX_CTAS", "8"))
     kinds = {"gather": None, "gather_capped_nccl_ctas": "capped", "gather_peer": "peer"}
-    # Default: the ring only.  The gather variants pass every test (CPU ranks, virtual ranks on one GPU, NCCL / peer memory on 2 and 8
-    # GPUs) and measure within 1 % of the ring at 2 GPUs, but the NCCL-transport one ended in an unexplained launch failure in two of
-    # two 8-GPU bench runs — opt in with FA_BENCH_CP_VARIANTS=gather_peer,gather.
-    wanted = [v for v in os.environ.get("FA_BENCH_CP_VARIANTS", "").split(",") if v in kinds]
+    # Default: the ring, then the gather variant over peer memory (the ring's result is saved first).  The NCCL-transport gather ended
+    # in an unexplained launch failure in two of two 8-GPU bench runs made before the staging race of DESIGN.md §4b was fixed (clean
+    # at 2 and 4 GPUs after the fix; not re-run at 8) — opt in with FA_BENCH_CP_VARIANTS=gather_peer,gather; "none" = ring only.
+    wanted = [v for v in os.environ.get("FA_BENCH_CP_VARIANTS", "gather_peer").split(",") if v in kinds]
     if "gather_capped_nccl_ctas" in wanted:
         # creating another NCCL communicator AFTER symmetric-memory buffers were exchanged on the default group ended in a launch
         # failure on this stack (torch 2.11 / NCCL 2.28): the peer-memory variant goes last then
